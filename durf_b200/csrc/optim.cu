@@ -1,0 +1,71 @@
+// KA -- gradient post-processing and Adam (train_boxpose.py:262-288; flax.optim.Adam).
+// Two multi-tensor passes over the flat parameter blob: sanitise + clip + sum of squares, then the global-norm
+// scale folded into the Adam update.  HBM-bound: 8 B + 28 B per parameter.
+#include "common.cuh"
+
+namespace durf {
+
+// jnp.nan_to_num(g, posinf=0.0): NaN -> 0, +inf -> 0, -inf -> -FLT_MAX; then clip to +-max_val (if > 0).
+__global__ void __launch_bounds__(256)
+grad_sanitize_kernel(int64_t n, float* __restrict__ g, float max_val, float scale, float* __restrict__ sumsq) {
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = g[i] * scale;
+    if (v != v) v = 0.f;
+    else if (isinf(v)) v = v > 0.f ? 0.f : -3.402823466e+38f;
+    if (max_val > 0.f) v = fminf(fmaxf(v, -max_val), max_val);
+    g[i] = v;
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(sumsq, t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            const float* __restrict__ sumsq, float max_norm, float lr, float b1, float b2, float eps, float c1, float c2) {
+  float mult = 1.f;
+  if (max_norm > 0.f) mult = fminf(1.f, max_norm / (1e-7f + sqrtf(*sumsq)));   // train_boxpose.py:283-285
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = mult * g[i];
+    const float mi = (1.f - b1) * gi + b1 * m[i];
+    const float vi = (1.f - b2) * (gi * gi) + b2 * v[i];
+    m[i] = mi;
+    v[i] = vi;
+    const float mhat = mi / c1;
+    const float denom = sqrtf(vi / c2) + eps;
+    p[i] = p[i] - lr * mhat / denom;
+  }
+}
+
+}  // namespace durf
+
+using namespace durf;
+
+extern "C" int durf_grad_sanitize(durf_stream_t stream, int64_t n, float* grad, float max_val, float grad_scale, float* sumsq) {
+  DURF_REQUIRE(n >= 0 && grad && sumsq, DURF_E_INVALID, "durf_grad_sanitize: bad argument");
+  if (n == 0) return DURF_OK;
+  const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  grad_sanitize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, grad, max_val, grad_scale, sumsq);
+  DURF_CHECK_LAUNCH("durf_grad_sanitize");
+  return DURF_OK;
+}
+
+extern "C" int durf_adam_step(durf_stream_t stream, int64_t n, float* params, const float* grad, float* m, float* v,
+                              const float* sumsq, float max_norm, float lr, float beta1, float beta2, float eps, int32_t step) {
+  DURF_REQUIRE(n >= 0 && params && grad && m && v && sumsq && step >= 0, DURF_E_INVALID, "durf_adam_step: bad argument");
+  if (n == 0) return DURF_OK;
+  const double t = (double)step + 1.0;
+  const float c1 = (float)(1.0 - pow((double)beta1, t)), c2 = (float)(1.0 - pow((double)beta2, t));
+  const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, params, grad, m, v, sumsq, max_norm, lr, beta1, beta2, eps, c1, c2);
+  DURF_CHECK_LAUNCH("durf_adam_step");
+  return DURF_OK;
+}

@@ -1,0 +1,333 @@
+"""Host-side mirror of the reference's internal/obbpose_model.py, driving the CUDA kernels.
+
+`MipNerfModel.apply(variables, rng, rays, init, ext, ts, randomized, rand_bkgd, white_bkgd, alpha)` keeps the
+argument order and the per-level 10-tuple of MipNerfModel.__call__ (obbpose_model.py:69-261); `render_image`
+keeps obbpose_model.py:421-479.  Tensors are torch CUDA tensors instead of jnp arrays.
+
+Differences that are part of the boundary (documented in INTEGRATION.md):
+  * `rng` carries the explicit random buffers (the reference's threefry streams cannot be reproduced without JAX):
+    a dict with optional 't_rand' [B,N+1], 'u_rand' [B,N+1], 'density_noise' [L][B,N]; or a torch.Generator / None,
+    in which case the buffers are drawn on the device.
+  * parameters live in one flat fp32 tensor (`Variables.flat`) with named views, so the optimizer and the gradient
+    all-reduce are single launches; `Variables.to_flax_dict()` gives the reference's params/MLP_0/Dense_i/{kernel,bias}.
+  * object MLPs run only on the rays that hit their box (result-identical to the reference's evaluate-everything-and-
+    mask, obbpose_model.py:174-201, because masked rows are multiplied by 0).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, NamedTuple, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from .utils import Rays
+
+
+@dataclass
+class MipNerfModel:
+    """Fields and defaults of the reference's gin-configurable MipNerfModel (obbpose_model.py:45-66); the values of
+    configs/carla_dyn.gin are the defaults here where the gin file overrides the class default."""
+    num_samples: int = 128
+    num_levels: int = 2
+    resample_padding: float = 0.01
+    stop_level_grad: bool = True
+    use_viewdirs: bool = True
+    lindisp: bool = False
+    ray_shape: str = 'cone'
+    min_deg_point: int = 0
+    max_deg_point: int = 10
+    deg_view: int = 4
+    num_objects: int = 2
+    density_noise: float = 0.0
+    density_bias: float = -1.0
+    rgb_padding: float = 0.001
+    disable_integration: bool = False
+    contraction: bool = True
+    dynamics: bool = True
+    timesteps: int = 5
+    no_pose_opt: bool = True
+    no_yaw_opt: bool = True
+    # MLP / BoxMLP shapes (obbpose_model.py:294-303, 358-367 + gin)
+    net_width: int = 256
+    box_net_width: int = 128
+    net_depth: int = 8
+    skip_layer: int = 4
+    net_width_condition: int = 128
+    # which MLP kernels to use: 'bf16' = tcgen05 chain (throughput), 'fp32' = CUDA-core parity mode
+    precision: str = 'bf16'
+
+    # -- topology helpers ------------------------------------------------------------------------------
+    def bg_topology(self):
+        return (6 * (self.max_deg_point - self.min_deg_point), self.net_width, self.net_depth, self.skip_layer,
+                3 + 6 * self.deg_view, self.net_width_condition)
+
+    def box_topology(self):
+        return (3 + 6 * (self.max_deg_point - self.min_deg_point), self.box_net_width, self.net_depth, self.skip_layer,
+                3 + 6 * self.deg_view, self.net_width_condition)
+
+    # -- parameters --------------------------------------------------------------------------------------
+    def init(self, rng: np.random.Generator, box_centers_init, device='cuda', bias_scale: float = 0.0) -> "Variables":
+        """construct_mipnerf / model.init (obbpose_model.py:264-291): glorot-uniform kernels, zero biases,
+        box_centers <- init (init_boxes, :35-39)."""
+        from .synthetic import glorot_mlp
+        init = np.asarray(box_centers_init, np.float32)
+        if init.ndim < 3:
+            init = init[:, None, :]
+        K = init.shape[1]
+        v = Variables.allocate(self, K, init.shape[0], device)
+        bt, ot = self.bg_topology(), self.box_topology()
+        v.load_mlp('MLP_0', glorot_mlp(rng, bt[0], bt[1], bias_scale, depth=bt[2], skip=bt[3], cond_dim=bt[4], cond_width=bt[5]))
+        for k in range(K):
+            v.load_mlp(f'BoxMLP_{k}', glorot_mlp(rng, ot[0], ot[1], bias_scale, depth=ot[2], skip=ot[3], cond_dim=ot[4],
+                                                 cond_width=ot[5]))
+        v.box_centers.copy_(torch.from_numpy(init).to(device))
+        v.mark_dirty()
+        return v
+
+    # -- forward -----------------------------------------------------------------------------------------
+    def apply(self, variables: "Variables", rng, rays: Rays, init, ext, ts, randomized: bool, rand_bkgd: bool,
+              white_bkgd: bool, alpha: float, ctx: Optional[dict] = None):
+        """MipNerfModel.__call__ (obbpose_model.py:69-261).  `init` is accepted for signature parity (the box
+        parameters live in `variables`, as `self.param('box_centers', ...)` does after initialisation).
+        When `ctx` (a dict) is given the forward keeps what the backward pass needs in it."""
+        prec = L.PREC_BF16 if self.precision == 'bf16' else L.PREC_FP32
+        if ctx is not None and prec != L.PREC_FP32:
+            raise L.DurfError("training (ctx != None) runs the MLPs in precision='fp32' in this build")
+        N = self.num_samples
+        origins, dirs = ops.f32(rays.origins), ops.f32(rays.directions)
+        B = origins.shape[0]
+        dev = origins.device
+        ts_i = int(ts.reshape(-1)[0].item()) if torch.is_tensor(ts) else int(np.asarray(ts).reshape(-1)[0])
+        box = variables.box_centers[ts_i].contiguous()                       # [K,6]
+        K = box.shape[0]
+        ext = ops.f32(torch.as_tensor(ext, device=dev)).reshape(K, 3)
+        rb = _rand_buffers(rng, randomized, B, N, self.num_levels, self.density_noise, dev)
+
+        fe = ops.obb_frontend(origins, dirs, box, ext)
+        origins_s, dirs_s, hit = fe['origins_s'], fe['dirs_s'], fe['hit']
+        viewenc = ops.viewdir_enc(rays.viewdirs, self.deg_view)
+        radii = ops.f32(rays.radii).reshape(-1)
+
+        obj_lists = []
+        bg_mult = None
+        if self.dynamics:
+            bg_mult = 1.0 - fe['nhit']                                       # 1 - sum_k mask_k (obbpose_model.py:205)
+            for k in range(K):
+                idx, cnt = ops.compact_hits(hit, k)
+                m_host = None
+                if prec == L.PREC_FP32:
+                    m_host = int(cnt.item())                                 # parity mode sizes its buffers exactly
+                obj_lists.append((idx, cnt, m_host))
+        bt, ot = self.bg_topology(), self.box_topology()
+        bf16 = prec == L.PREC_BF16
+        if bf16:
+            variables.ensure_packed(self)
+
+        ret = []
+        t_vals = weights = None
+        if ctx is not None:
+            ctx.update(dict(fe=fe, viewenc=viewenc, obj_lists=obj_lists, levels=[], B=B, K=K, ts=ts_i, alpha=alpha,
+                            white_bkgd=white_bkgd, rand_bkgd=rand_bkgd, rays=rays, box=box, radii=radii))
+        for i_level in range(self.num_levels):
+            common = dict(min_deg=self.min_deg_point, max_deg=self.max_deg_point, ray_shape=self.ray_shape,
+                          integrate=not self.disable_integration, bf16_tiles=bf16)
+            if i_level == 0:
+                rm = ops.raymarch(origins_s, dirs_s, radii, N, near=rays.near, far=rays.far, t_rand=rb['t_rand'],
+                                  contract=self.contraction, ray_mult=bg_mult, **common)
+                t_vals = rm['t_vals']
+            else:
+                t_vals = ops.resample(t_vals, weights, u_rand=rb['u_rand'], padding=self.resample_padding)
+                rm = ops.raymarch(origins_s, dirs_s, radii, N, t_vals=t_vals, contract=self.contraction, ray_mult=bg_mult,
+                                  **common)
+            raw_rgb, raw_density, saved_bg = ops.mlp_fwd(bt, rm['features'], viewenc, variables.blob('MLP_0'), M=B, N=N,
+                                                         precision=prec, packed=variables.packed.get('MLP_0'),
+                                                         save=ctx is not None)
+            lvl_ctx = dict(feat_bg=rm['features'], saved_bg=saved_bg, obj=[]) if ctx is not None else None
+            if self.dynamics:
+                for k, (idx, cnt, m_host) in enumerate(obj_lists):
+                    if m_host == 0:
+                        if lvl_ctx is not None:
+                            lvl_ctx['obj'].append(None)
+                        continue
+                    rows = m_host if m_host is not None else B
+                    rmo = ops.raymarch(origins_s, dirs_s, radii, N, t_vals=t_vals, weighted=True, alpha=alpha, ray_index=idx,
+                                       count=None if m_host is not None else cnt, rows=rows, **common)
+                    _, _, saved_o = ops.mlp_fwd(ot, rmo['features'], viewenc, variables.blob(f'BoxMLP_{k}'), M=rows, N=N,
+                                                precision=prec, packed=variables.packed.get(f'BoxMLP_{k}'), ray_index=idx,
+                                                count=None if m_host is not None else cnt, accumulate=True, raw_rgb=raw_rgb,
+                                                raw_density=raw_density, save=ctx is not None)
+                    if lvl_ctx is not None:
+                        lvl_ctx['obj'].append(dict(feat=rmo['features'], saved=saved_o, rows=rows))
+            if randomized and self.density_noise > 0:
+                raw_density = raw_density + self.density_noise * rb['density_noise'][i_level]   # obbpose_model.py:237-240
+            comp = ops.composite(raw_rgb, raw_density, t_vals, dirs_s, white_bkgd=white_bkgd, rand_bkgd=rand_bkgd,
+                                 density_bias=self.density_bias)
+            weights = comp['weights']
+            dyn_mask = fe['nhit'].reshape(B, 1)
+            ret.append((comp['comp_rgb'], comp['depth'], comp['acc'], weights, t_vals, comp['t_mids'], comp['t_dists'],
+                        [box[:, :3], box[:, 3:]], dyn_mask, fe['zo_ret']))
+            if lvl_ctx is not None:
+                lvl_ctx.update(raw_rgb=raw_rgb, raw_density=raw_density, t_vals=t_vals)
+                ctx['levels'].append(lvl_ctx)
+        return ret
+
+    # -- backward ----------------------------------------------------------------------------------------
+    def backward(self, variables: "Variables", ctx: dict, level_grads: Sequence[dict], d_flat: torch.Tensor) -> None:
+        """Reverse of `apply` (what jax.value_and_grad does through model.apply, train_boxpose.py:251): given per level
+        dL/d(comp_rgb, depth, weights) accumulate dL/d parameters into `d_flat` (same layout as variables.flat).
+        Levels are independent: t_vals are stop_gradient'ed (mip.py:413-414)."""
+        N = self.num_samples
+        fe, viewenc = ctx['fe'], ctx['viewenc']
+        B, K = ctx['B'], ctx['K']
+        bt, ot = self.bg_topology(), self.box_topology()
+        pose_opt = self.dynamics and not (self.no_pose_opt and self.no_yaw_opt)
+        d_os = torch.zeros(B, 3, device=d_flat.device) if pose_opt else None
+        d_ds = torch.zeros(B, 3, device=d_flat.device) if pose_opt else None
+        for lvl, g in zip(ctx['levels'], level_grads):
+            g_rgb, g_den, g_dirs = ops.composite_bwd(lvl['raw_rgb'], lvl['raw_density'], lvl['t_vals'], fe['dirs_s'],
+                                                     g['comp_rgb'], g['depth'], g['weights'], white_bkgd=ctx['white_bkgd'],
+                                                     rand_bkgd=ctx['rand_bkgd'], density_bias=self.density_bias,
+                                                     want_d_dirs=pose_opt)
+            ops.mlp_bwd(bt, lvl['feat_bg'], viewenc, variables.blob('MLP_0'), lvl['saved_bg'], g_rgb, g_den,
+                        variables.blob_of(d_flat, 'MLP_0'), M=B, N=N)
+            if pose_opt:
+                d_ds += g_dirs * (fe['nhit'] > 0).float()[:, None]            # only object rays carry pose-dependent dirs
+            for k, o in enumerate(lvl['obj']):
+                if o is None:
+                    continue
+                idx = ctx['obj_lists'][k][0]
+                dfeat = ops.mlp_bwd(ot, o['feat'], viewenc, variables.blob(f'BoxMLP_{k}'), o['saved'], g_rgb, g_den,
+                                    variables.blob_of(d_flat, f'BoxMLP_{k}'), M=o['rows'], N=N, ray_index=idx,
+                                    want_d_features=pose_opt)
+                if pose_opt:
+                    go = torch.zeros(B, 3, device=d_flat.device)
+                    gd = torch.zeros(B, 3, device=d_flat.device)
+                    ops.raymarch_bwd(fe['origins_s'], fe['dirs_s'], ctx['radii'], lvl['t_vals'], dfeat, weighted=True,
+                                     alpha=ctx['alpha'], min_deg=self.min_deg_point, max_deg=self.max_deg_point, ray_index=idx,
+                                     rows=o['rows'], d_origins=go, d_dirs=gd)
+                    d_os += go
+                    d_ds += gd
+        if pose_opt:
+            d_box = torch.zeros(K, 6, device=d_flat.device)
+            ops.obb_frontend_bwd(ctx['rays'].origins, ctx['rays'].directions, ctx['box'], fe['hit'], d_os, d_ds,
+                                 pose_grad=not self.no_pose_opt, rot_grad=not self.no_yaw_opt, d_box=d_box)
+            variables.view_of(d_flat, 'box_centers')[ctx['ts']] += d_box
+
+
+def _rand_buffers(rng, randomized: bool, B: int, N: int, levels: int, density_noise: float, dev) -> dict:
+    out = dict(t_rand=None, u_rand=None, density_noise=None)
+    if not randomized:
+        return out
+    if isinstance(rng, dict):
+        out.update({k: (None if v is None else v) for k, v in rng.items() if k in out})
+        gen = None
+    else:
+        gen = rng if isinstance(rng, torch.Generator) else None
+    if out['t_rand'] is None:
+        out['t_rand'] = torch.rand(B, N + 1, device=dev, generator=gen)
+    if out['u_rand'] is None:
+        out['u_rand'] = torch.rand(B, N + 1, device=dev, generator=gen)
+    if density_noise > 0 and out['density_noise'] is None:
+        out['density_noise'] = [torch.randn(B, N, device=dev, generator=gen) for _ in range(levels)]
+    return out
+
+
+class Variables:
+    """All trainable parameters in ONE flat fp32 device tensor: [MLP_0 | BoxMLP_0 .. BoxMLP_{K-1} | box_centers].
+    Names follow the reference's flax tree (params/MLP_0, params/BoxMLP_k, params/box_centers)."""
+
+    def __init__(self, flat: torch.Tensor, slots: Dict[str, Tuple[int, int]], topo: Dict[str, tuple], T: int, K: int):
+        self.flat = flat
+        self.slots = slots
+        self.topo = topo
+        self.T, self.K = T, K
+        self.packed: Dict[str, torch.Tensor] = {}
+        self._dirty = True
+
+    @staticmethod
+    def allocate(model: MipNerfModel, K: int, T: int, device) -> "Variables":
+        slots, topo, off = {}, {}, 0
+        names = [('MLP_0', model.bg_topology())] + [(f'BoxMLP_{k}', model.box_topology()) for k in range(K)]
+        for name, t in names:
+            n = ops.mlp_param_count(t)
+            slots[name] = (off, n)
+            topo[name] = t
+            off += n
+        slots['box_centers'] = (off, T * K * 6)
+        off += T * K * 6
+        return Variables(torch.zeros(off, device=device, dtype=torch.float32), slots, topo, T, K)
+
+    # views
+    def blob_of(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        o, n = self.slots[name]
+        return flat[o:o + n]
+
+    def view_of(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        v = self.blob_of(flat, name)
+        return v.view(self.T, self.K, 6) if name == 'box_centers' else v
+
+    def blob(self, name: str) -> torch.Tensor:
+        return self.blob_of(self.flat, name)
+
+    @property
+    def box_centers(self) -> torch.Tensor:
+        return self.view_of(self.flat, 'box_centers')
+
+    def layers(self, name: str, flat: Optional[torch.Tensor] = None):
+        return ops.mlp_layer_views(self.topo[name], self.blob_of(self.flat if flat is None else flat, name))
+
+    def load_mlp(self, name: str, layers) -> None:
+        for (w, b), (kw, kb) in zip(self.layers(name), layers):
+            w.copy_(torch.as_tensor(kw)); b.copy_(torch.as_tensor(kb))
+        self._dirty = True
+
+    def mark_dirty(self) -> None:
+        self._dirty = True
+
+    def ensure_packed(self, model: MipNerfModel) -> None:
+        """(Re)build the tensor-core weight images after the parameters changed."""
+        if not self._dirty and self.packed:
+            return
+        for name, t in self.topo.items():
+            self.packed[name] = ops.mlp_pack(t, self.blob(name), self.packed.get(name))
+        self._dirty = False
+
+    def to_flax_dict(self) -> Dict[str, Any]:
+        """The reference's parameter tree: params/{MLP_0,BoxMLP_k}/Dense_i/{kernel,bias}, params/box_centers."""
+        tree: Dict[str, Any] = {}
+        for name in self.topo:
+            tree[name] = {f'Dense_{i}': {'kernel': w, 'bias': b} for i, (w, b) in enumerate(self.layers(name))}
+        tree['box_centers'] = self.box_centers
+        return {'params': tree}
+
+
+def construct_mipnerf(rng: np.random.Generator, example_batch: dict, device='cuda', **model_kwargs):
+    """obbpose_model.py:264-291: build the model and its variables from an example batch (uses 'init')."""
+    model = MipNerfModel(**model_kwargs)
+    init = np.asarray(example_batch['init'], np.float32).squeeze()
+    return model, model.init(rng, init, device=device)
+
+
+def render_image(render_fn, rays: Rays, init, ext, ts, rng, alpha, chunk: int = 8192):
+    """obbpose_model.py:421-479: render all pixels of a frame in `chunk`-ray slices; returns the fine level's
+    (rgb[H,W,3], distance[H,W], acc[H,W]).  `render_fn(rng, batch)` returns the model's per-level list, like the
+    reference's pmapped render_eval_pfn.  Rays may live on the host (pinned) or on the device; every chunk is moved
+    with non-blocking copies on the current stream, results stay on the device until the end (one sync per frame,
+    not one per chunk)."""
+    height, width = rays[0].shape[:2]
+    num_rays = height * width
+    flat = Rays(*[r.reshape(num_rays, -1) for r in rays])
+    dev = torch.device('cuda')
+    rgb = torch.empty(num_rays, 3, device=dev)
+    dist = torch.empty(num_rays, device=dev)
+    acc = torch.empty(num_rays, device=dev)
+    for i in range(0, num_rays, chunk):
+        chunk_rays = Rays(*[r[i:i + chunk].to(dev, non_blocking=True) for r in flat])
+        batch = dict(rays=chunk_rays, init=init, ext=ext, ts=ts, alpha=alpha)
+        out = render_fn(rng, batch)[-1]
+        n = chunk_rays.origins.shape[0]
+        rgb[i:i + n] = out[0]; dist[i:i + n] = out[1]; acc[i:i + n] = out[2]
+    return rgb.reshape(height, width, 3), dist.reshape(height, width), acc.reshape(height, width)

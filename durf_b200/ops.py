@@ -1,0 +1,307 @@
+"""One Python function per C-ABI entry point: allocates outputs with torch, passes raw device pointers.
+
+This is the lowest host layer; `mip.py`, `mip360.py`, `box_helpers.py`, `math.py`, `obbpose_model.py` and
+`train.py` (the mirrors of the reference's modules) are written on top of it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import MlpTopology, check, f32, ptr, stream_ptr
+
+BG_TOPOLOGY = (60, 256, 8, 4, 27, 128)    # MLP, configs/carla_dyn.gin:55-58
+BOX_TOPOLOGY = (63, 128, 8, 4, 27, 128)   # BoxMLP defaults, obbpose_model.py:360-363
+
+
+def topology(t) -> MlpTopology:
+    return t if isinstance(t, MlpTopology) else MlpTopology(*t)
+
+
+def _dev(t: torch.Tensor):
+    if not t.is_cuda:
+        raise L.DurfError("durf_b200 needs CUDA tensors; there is no CPU path")
+    return t.device
+
+
+def launch_count() -> int:
+    return int(L.load().durf_launch_count())
+
+
+def reset_launch_count() -> None:
+    L.load().durf_reset_launch_count()
+
+
+# ---- K0 ---------------------------------------------------------------------------------------------
+def aa2matrix(angles: torch.Tensor) -> torch.Tensor:
+    angles = f32(angles)
+    K = angles.shape[0]
+    R = torch.empty(K, 3, 3, device=_dev(angles), dtype=torch.float32)
+    check(L.load().durf_aa2matrix_fwd(stream_ptr(), K, ptr(angles), ptr(R)), "durf_aa2matrix_fwd")
+    return R
+
+
+def obb_frontend(origins, directions, box, ext, want_object_rays: bool = False):
+    """-> dict(origins_s, dirs_s, hit[B,K] i32, zi, zo, zo_ret[B], nhit[B], [origins_o, dirs_o])."""
+    origins, directions, box, ext = f32(origins), f32(directions), f32(box), f32(ext)
+    B, K = origins.shape[0], box.shape[0]
+    dev = _dev(origins)
+    o = dict(origins_s=torch.empty(B, 3, device=dev), dirs_s=torch.empty(B, 3, device=dev),
+             hit=torch.empty(B, K, device=dev, dtype=torch.int32), zi=torch.empty(B, K, device=dev),
+             zo=torch.empty(B, K, device=dev), zo_ret=torch.empty(B, device=dev), nhit=torch.empty(B, device=dev))
+    oo = torch.empty(B, K, 3, device=dev) if want_object_rays else None
+    do = torch.empty(B, K, 3, device=dev) if want_object_rays else None
+    check(L.load().durf_obb_frontend_fwd(stream_ptr(), B, K, ptr(origins), ptr(directions), ptr(box), ptr(ext),
+                                         ptr(o['origins_s']), ptr(o['dirs_s']), ptr(o['hit']), ptr(o['zi']), ptr(o['zo']),
+                                         ptr(o['zo_ret']), ptr(o['nhit']), ptr(oo), ptr(do)), "durf_obb_frontend_fwd")
+    if want_object_rays:
+        o['origins_o'], o['dirs_o'] = oo, do
+    return o
+
+
+def obb_frontend_bwd(origins, directions, box, hit, d_origins_s, d_dirs_s, pose_grad: bool, rot_grad: bool, d_box):
+    B, K = origins.shape[0], box.shape[0]
+    check(L.load().durf_obb_frontend_bwd(stream_ptr(), B, K, ptr(f32(origins)), ptr(f32(directions)), ptr(f32(box)), ptr(hit),
+                                         ptr(d_origins_s), ptr(d_dirs_s), int(pose_grad), int(rot_grad), ptr(d_box)),
+          "durf_obb_frontend_bwd")
+
+
+def compact_hits(hit: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    B, K = hit.shape
+    idx = torch.empty(B, device=hit.device, dtype=torch.int32)
+    cnt = torch.empty(1, device=hit.device, dtype=torch.int32)
+    check(L.load().durf_compact_hits(stream_ptr(), B, K, k, ptr(hit), ptr(idx), ptr(cnt)), "durf_compact_hits")
+    return idx, cnt
+
+
+# ---- K1 ---------------------------------------------------------------------------------------------
+def raymarch(origins, dirs, radii, N: int, *, t_vals=None, near=None, far=None, t_rand=None, contract=False,
+             weighted=False, alpha=0.0, min_deg=0, max_deg=10, ray_shape='cone', integrate=True, ray_mult=None,
+             ray_index=None, count=None, rows=None, bf16_tiles=False, want_gaussians=False):
+    """Fused sample/cast/contract/encode.  Returns dict(t_vals, features, [means, cov_diag])."""
+    if ray_shape not in ('cone', 'cylinder'):
+        raise AssertionError("ray_shape must be 'cone' or 'cylinder'")          # mip.py:176 `assert False`
+    origins, dirs = f32(origins), f32(dirs)
+    radii = f32(radii).reshape(-1)
+    B = origins.shape[0]
+    dev = _dev(origins)
+    flags = 0
+    if t_vals is None:
+        flags |= L.RM_SAMPLE
+        t_vals = torch.empty(B, N + 1, device=dev)
+        near, far = f32(near).reshape(-1), f32(far).reshape(-1)
+        if t_rand is not None:
+            flags |= L.RM_RANDOMIZED
+            t_rand = f32(t_rand)
+    else:
+        t_vals = f32(t_vals)
+    if contract: flags |= L.RM_CONTRACT
+    if weighted: flags |= L.RM_WEIGHTED
+    if ray_shape == 'cylinder': flags |= L.RM_CYLINDER
+    if not integrate: flags |= L.RM_NO_INTEGRATE
+    if bf16_tiles: flags |= L.RM_OUT_BF16_TILE
+    F = 6 * (max_deg - min_deg) + (3 if weighted else 0)
+    M = B if rows is None else rows          # rows of the output buffers (compacted calls may pass fewer)
+    if bf16_tiles:
+        tiles = (M * N + 127) // 128
+        feats = torch.empty(tiles, 128 * 64, device=dev, dtype=torch.bfloat16)
+    else:
+        feats = torch.empty(M, N, F, device=dev)
+    means = torch.empty(M, N, 3, device=dev) if want_gaussians else None
+    covd = torch.empty(M, N, 3, device=dev) if want_gaussians else None
+    a = L.RaymarchArgs(B=M, N=N, min_deg=min_deg, max_deg=max_deg, flags=flags, alpha=float(alpha),
+                       origins=ptr(origins), dirs=ptr(dirs), radii=ptr(radii), near=ptr(near), far=ptr(far),
+                       t_rand=ptr(t_rand), t_vals=ptr(t_vals), ray_mult=ptr(ray_mult), ray_index=ptr(ray_index),
+                       count=ptr(count), features=ptr(feats), means=ptr(means), cov_diag=ptr(covd))
+    check(L.load().durf_raymarch_fwd(stream_ptr(), C.byref(a)), "durf_raymarch_fwd")
+    out = dict(t_vals=t_vals, features=feats)
+    if want_gaussians:
+        out['means'], out['cov_diag'] = means, covd
+    return out
+
+
+def raymarch_bwd(origins, dirs, radii, t_vals, d_features, *, weighted, alpha, min_deg=0, max_deg=10, ray_mult=None,
+                 ray_index=None, rows=None, d_origins=None, d_dirs=None):
+    """Gradient of the object-frame encoding w.r.t. origins_s / dirs_s (written for the rays in ray_index)."""
+    B = origins.shape[0]
+    N = t_vals.shape[1] - 1
+    M = B if rows is None else rows
+    flags = L.RM_WEIGHTED if weighted else 0
+    a = L.RaymarchArgs(B=M, N=N, min_deg=min_deg, max_deg=max_deg, flags=flags, alpha=float(alpha),
+                       origins=ptr(f32(origins)), dirs=ptr(f32(dirs)), radii=ptr(f32(radii).reshape(-1)), near=None, far=None,
+                       t_rand=None, t_vals=ptr(f32(t_vals)), ray_mult=ptr(ray_mult), ray_index=ptr(ray_index), count=None,
+                       features=ptr(d_features), means=None, cov_diag=None)
+    check(L.load().durf_raymarch_bwd(stream_ptr(), C.byref(a), ptr(f32(d_features)), ptr(d_origins), ptr(d_dirs)),
+          "durf_raymarch_bwd")
+
+
+def viewdir_enc(viewdirs: torch.Tensor, deg: int = 4) -> torch.Tensor:
+    viewdirs = f32(viewdirs)
+    B = viewdirs.shape[0]
+    enc = torch.empty(B, 3 + 6 * deg, device=_dev(viewdirs))
+    check(L.load().durf_viewdir_enc_fwd(stream_ptr(), B, deg, ptr(viewdirs), ptr(enc)), "durf_viewdir_enc_fwd")
+    return enc
+
+
+# ---- K2 ---------------------------------------------------------------------------------------------
+def mlp_param_count(topo) -> int:
+    return int(L.load().durf_mlp_param_count(C.byref(topology(topo))))
+
+
+def mlp_layer_views(topo, blob: torch.Tensor):
+    """[(kernel[in,out], bias[out])] views into a flat fp32 parameter blob (Dense_0 .. Dense_{depth+3})."""
+    t = topology(topo)
+    lib = L.load()
+    out = []
+    for i in range(t.depth + 4):
+        ki, ko = C.c_int32(), C.c_int32()
+        off = int(lib.durf_mlp_param_offset(C.byref(t), i, C.byref(ki), C.byref(ko)))
+        w = blob[off: off + ki.value * ko.value].view(ki.value, ko.value)
+        b = blob[off + ki.value * ko.value: off + ki.value * ko.value + ko.value]
+        out.append((w, b))
+    return out
+
+
+def mlp_pack(topo, blob: torch.Tensor, packed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 blob -> tensor-core weight image (bf16, pre-tiled, pre-swizzled)."""
+    t = topology(topo)
+    nbytes = int(L.load().durf_mlp_packed_bytes(C.byref(t)))
+    if nbytes <= 0:
+        raise L.DurfError("this MLP topology has no tensor-core path")
+    if packed is None:
+        packed = torch.empty(nbytes, device=_dev(blob), dtype=torch.uint8)
+    check(L.load().durf_mlp_pack_weights(stream_ptr(), C.byref(t), ptr(f32(blob)), ptr(packed)), "durf_mlp_pack_weights")
+    return packed
+
+
+def _mlp_args(topo, precision, M, N, features, cond, blob, packed, ray_index, count, accumulate, raw_rgb, raw_density, saved,
+              workspace):
+    return L.MlpArgs(topo=topology(topo), precision=precision, M=M, N=N, features=ptr(features), cond=ptr(cond),
+                     params=ptr(blob), packed=ptr(packed), ray_index=ptr(ray_index), count=ptr(count),
+                     accumulate=int(accumulate), raw_rgb=ptr(raw_rgb), raw_density=ptr(raw_density), saved=ptr(saved),
+                     workspace=ptr(workspace), workspace_bytes=0 if workspace is None else workspace.numel() * workspace.element_size())
+
+
+def mlp_fwd(topo, features, cond, blob, *, M: int, N: int, precision=L.PREC_BF16, packed=None, ray_index=None, count=None,
+            accumulate=False, raw_rgb=None, raw_density=None, num_rays_out=None, save=False):
+    """Returns (raw_rgb[B,N,3], raw_density[B,N], saved-or-None)."""
+    t = topology(topo)
+    dev = _dev(features)
+    Bout = num_rays_out if num_rays_out is not None else M
+    if raw_rgb is None:
+        raw_rgb = torch.empty(Bout, N, 3, device=dev)
+        raw_density = torch.empty(Bout, N, device=dev)
+    lib = L.load()
+    saved = ws = None
+    if precision == L.PREC_FP32:
+        if save:
+            saved = torch.empty(int(lib.durf_mlp_saved_bytes(C.byref(t), precision, M, N)) // 4, device=dev)
+        else:
+            ws = torch.empty(int(lib.durf_mlp_workspace_bytes(C.byref(t), precision, M, N, 0)) // 4, device=dev)
+    a = _mlp_args(t, precision, M, N, features, f32(cond), f32(blob), packed, ray_index, count, accumulate, raw_rgb, raw_density,
+                  saved, ws)
+    check(lib.durf_mlp_fwd(stream_ptr(), C.byref(a)), "durf_mlp_fwd")
+    return raw_rgb, raw_density, saved
+
+
+def mlp_bwd(topo, features, cond, blob, saved, d_raw_rgb, d_raw_density, d_blob, *, M: int, N: int, ray_index=None,
+            want_d_features=False):
+    """Accumulates into d_blob; returns d_features [M*N, in_dim] or None."""
+    t = topology(topo)
+    dev = _dev(features)
+    lib = L.load()
+    ws = torch.empty(int(lib.durf_mlp_workspace_bytes(C.byref(t), L.PREC_FP32, M, N, 1)) // 4, device=dev)
+    dfeat = torch.empty(M * N, t.in_dim, device=dev) if want_d_features else None
+    a = _mlp_args(t, L.PREC_FP32, M, N, features, f32(cond), f32(blob), None, ray_index, None, False, d_raw_rgb, d_raw_density,
+                  saved, ws)
+    check(lib.durf_mlp_bwd(stream_ptr(), C.byref(a), ptr(f32(d_raw_rgb)), ptr(f32(d_raw_density)), ptr(d_blob), ptr(dfeat)),
+          "durf_mlp_bwd")
+    return dfeat
+
+
+# ---- K3 ---------------------------------------------------------------------------------------------
+def _comp_args(raw_rgb, raw_density, t_vals, dirs, white_bkgd, rand_bkgd, activated, density_bias, outs):
+    B, N = raw_density.shape[0], raw_density.shape[1]
+    return L.CompositeArgs(B=B, N=N, white_bkgd=int(white_bkgd), rand_bkgd=int(rand_bkgd), activated=int(activated),
+                           density_bias=float(density_bias), raw_rgb=ptr(raw_rgb), raw_density=ptr(raw_density),
+                           t_vals=ptr(t_vals), dirs=ptr(dirs), comp_rgb=ptr(outs.get('comp_rgb')), depth=ptr(outs.get('depth')),
+                           acc=ptr(outs.get('acc')), weights=ptr(outs.get('weights')), t_mids=ptr(outs.get('t_mids')),
+                           t_dists=ptr(outs.get('t_dists')))
+
+
+def composite(raw_rgb, raw_density, t_vals, dirs, *, white_bkgd=False, rand_bkgd=False, activated=False, density_bias=-1.0,
+              want_mids=True):
+    raw_rgb, raw_density, t_vals, dirs = f32(raw_rgb), f32(raw_density), f32(t_vals), f32(dirs)
+    raw_density = raw_density.reshape(raw_density.shape[0], -1)
+    B, N = raw_density.shape
+    dev = _dev(raw_rgb)
+    outs = dict(comp_rgb=torch.empty(B, 3, device=dev), depth=torch.empty(B, device=dev), acc=torch.empty(B, device=dev),
+                weights=torch.empty(B, N, device=dev))
+    if want_mids:
+        outs['t_mids'] = torch.empty(B, N, device=dev)
+        outs['t_dists'] = torch.empty(B, N, device=dev)
+    a = _comp_args(raw_rgb, raw_density, t_vals, dirs, white_bkgd, rand_bkgd, activated, density_bias, outs)
+    check(L.load().durf_composite_fwd(stream_ptr(), C.byref(a)), "durf_composite_fwd")
+    return outs
+
+
+def composite_bwd(raw_rgb, raw_density, t_vals, dirs, d_comp_rgb, d_depth, d_weights, *, d_acc=None, white_bkgd=False,
+                  rand_bkgd=False, activated=False, density_bias=-1.0, want_d_dirs=False):
+    raw_rgb, raw_density, t_vals, dirs = f32(raw_rgb), f32(raw_density), f32(t_vals), f32(dirs)
+    raw_density = raw_density.reshape(raw_density.shape[0], -1)
+    B, N = raw_density.shape
+    dev = _dev(raw_rgb)
+    g_rgb = torch.empty(B, N, 3, device=dev)
+    g_den = torch.empty(B, N, device=dev)
+    g_dirs = torch.empty(B, 3, device=dev) if want_d_dirs else None
+    a = _comp_args(raw_rgb, raw_density, t_vals, dirs, white_bkgd, rand_bkgd, activated, density_bias, {})
+    check(L.load().durf_composite_bwd(stream_ptr(), C.byref(a), ptr(f32(d_comp_rgb)), ptr(f32(d_depth)), ptr(d_acc),
+                                      ptr(f32(d_weights)), ptr(g_rgb), ptr(g_den), ptr(g_dirs)), "durf_composite_bwd")
+    return g_rgb, g_den, g_dirs
+
+
+# ---- K4 ---------------------------------------------------------------------------------------------
+def resample(t_vals, weights, *, u_rand=None, padding=0.01, blurpool=True, num_samples=None):
+    t_vals, weights = f32(t_vals), f32(weights)
+    B, N = weights.shape
+    S = N + 1 if num_samples is None else num_samples
+    out = torch.empty(B, S, device=_dev(t_vals))
+    check(L.load().durf_resample_fwd(stream_ptr(), B, N, ptr(t_vals), ptr(weights), ptr(None if u_rand is None else f32(u_rand)),
+                                     float(padding), int(blurpool), S, ptr(out)), "durf_resample_fwd")
+    return out
+
+
+# ---- KL / KA ----------------------------------------------------------------------------------------
+def loss_args(level, num_levels, eps, cfg, lv, batch, depth_mask, partials, grads):
+    B, N = lv['weights'].shape
+    g = grads
+    return L.LossArgs(B=B, N=N, level=level, num_levels=num_levels, eps=float(eps),
+                      coarse_loss_mult=cfg.coarse_loss_mult, box_loss_mult=cfg.box_loss_mult,
+                      depth_loss_mult=cfg.depth_loss_mult, near_loss_mult=cfg.near_loss_mult,
+                      empty_loss_mult=cfg.empty_loss_mult, sky_loss_mult=cfg.sky_loss_mult, distortion_mult=1e-6,
+                      comp_rgb=ptr(lv['comp_rgb']), depth=ptr(lv['depth']), weights=ptr(lv['weights']), t_vals=ptr(lv['t_vals']),
+                      pixels=ptr(batch['pixels']), depth_gt=ptr(batch['depth']), sky=ptr(batch['sky']),
+                      lossmult=ptr(batch['lossmult']), dyn_mask=ptr(batch['dyn_mask']), zo=ptr(batch['zo']),
+                      depth_mask=ptr(depth_mask), partials=ptr(partials), d_comp_rgb=ptr(g.get('comp_rgb')),
+                      d_depth=ptr(g.get('depth')), d_weights=ptr(g.get('weights')))
+
+
+def losses_prepare(args: L.LossArgs, norms: torch.Tensor):
+    check(L.load().durf_losses_prepare(stream_ptr(), C.byref(args), ptr(norms)), "durf_losses_prepare")
+
+
+def losses_fwd_bwd(args: L.LossArgs, norms: torch.Tensor):
+    check(L.load().durf_losses_fwd_bwd(stream_ptr(), C.byref(args), ptr(norms)), "durf_losses_fwd_bwd")
+
+
+def grad_sanitize(grad: torch.Tensor, max_val: float, scale: float, sumsq: torch.Tensor):
+    check(L.load().durf_grad_sanitize(stream_ptr(), grad.numel(), ptr(grad), float(max_val), float(scale), ptr(sumsq)),
+          "durf_grad_sanitize")
+
+
+def adam_step(params, grad, m, v, sumsq, *, max_norm, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(L.load().durf_adam_step(stream_ptr(), params.numel(), ptr(params), ptr(grad), ptr(m), ptr(v), ptr(sumsq),
+                                  float(max_norm), float(lr), beta1, beta2, eps, int(step)), "durf_adam_step")

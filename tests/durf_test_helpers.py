@@ -1,0 +1,85 @@
+"""Shared fixtures: one synthetic scene, materialised for the oracle (torch CPU) and for the CUDA path."""
+import numpy as np
+import torch
+
+from durf_b200 import synthetic as S
+from oracle import durf_oracle as O
+
+
+def scene(B=256, K=2, seed=7, bias_scale=0.05, far=40.0, behind=False, N=128):
+    rng = np.random.default_rng(seed)
+    rays, c2w = S.random_rays(rng, B, far=far)
+    centers, ext = S.boxes_in_view(rng, c2w, K, behind=behind)
+    mlp = S.glorot_mlp(rng, 60, 256, bias_scale)
+    box_mlps = [S.glorot_mlp(rng, 63, 128, bias_scale) for _ in range(K)]
+    tg = S.targets(rng, B)
+    t_rand = rng.uniform(size=(B, N + 1)).astype(np.float32)
+    u_rand = rng.uniform(size=(B, N + 1)).astype(np.float32)
+    return dict(rays=rays, c2w=c2w, centers=centers, ext=ext, mlp=mlp, box_mlps=box_mlps, targets=tg, t_rand=t_rand,
+                u_rand=u_rand, B=B, K=K)
+
+
+def oracle_params(sc, dtype=torch.float32):
+    cv = lambda layers: [(torch.from_numpy(k).to(dtype), torch.from_numpy(b).to(dtype)) for k, b in layers]
+    return dict(mlp=cv(sc['mlp']), box_mlps=[cv(m) for m in sc['box_mlps']], box_centers=torch.from_numpy(sc['centers']).to(dtype))
+
+
+def oracle_rays(sc, dtype=torch.float32):
+    return O.Rays(*[torch.from_numpy(np.asarray(a)).to(dtype) for a in sc['rays']])
+
+
+def cuda_rays(sc):
+    from durf_b200.utils import Rays
+    return Rays(*[torch.from_numpy(np.asarray(a)).cuda() for a in sc['rays']])
+
+
+def cuda_variables(sc, model):
+    from durf_b200.obbpose_model import Variables
+    v = Variables.allocate(model, sc['K'], sc['centers'].shape[0], 'cuda')
+    v.load_mlp('MLP_0', sc['mlp'])
+    for k, m in enumerate(sc['box_mlps']):
+        v.load_mlp(f'BoxMLP_{k}', m)
+    v.box_centers.copy_(torch.from_numpy(sc['centers']).cuda())
+    v.mark_dirty()
+    return v
+
+
+def flat_oracle_grads(sc, variables, grads_by_name):
+    """Lay oracle gradients (dict name -> list[(dk, db)] / tensor) out like Variables.flat."""
+    flat = torch.zeros(variables.flat.numel(), dtype=torch.float64)
+    for name, (off, n) in variables.slots.items():
+        g = grads_by_name.get(name)
+        if g is None:
+            continue
+        if name == 'box_centers':
+            flat[off:off + n] = g.reshape(-1).double()
+        else:
+            flat[off:off + n] = torch.cat([torch.cat([dk.reshape(-1), db.reshape(-1)]) for dk, db in g]).double()
+    return flat
+
+
+def assert_close(got, want, rtol=1e-5, atol_scale=1.0, what=""):
+    """|a-b| <= rtol * max(|b|, atol_scale)  (SURVEY §7 tolerance form)."""
+    got = got.detach().double().cpu()
+    want = want.detach().double().cpu()
+    assert got.shape == want.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(want.shape)}"
+    tol = rtol * torch.clamp(want.abs(), min=atol_scale)
+    err = (got - want).abs()
+    bad = err > tol
+    if bad.any():
+        i = torch.argmax(err - tol)
+        raise AssertionError(f"{what}: {int(bad.sum())}/{bad.numel()} beyond tol; worst |d|={float(err.flatten()[i]):.3e} "
+                             f"want={float(want.flatten()[i]):.6e} got={float(got.flatten()[i]):.6e}")
+
+
+def unswizzle_tiles(tiles: torch.Tensor, rows: int, F: int) -> torch.Tensor:
+    """bf16 128x64 SWIZZLE_128B tile images -> [rows, F] float32."""
+    t = tiles.view(torch.bfloat16).reshape(-1, 128 * 64).float().cpu()
+    ntiles = t.shape[0]
+    r = torch.arange(128)
+    out = torch.empty(ntiles, 128, 64)
+    for c in range(8):
+        off = (r // 8) * 512 + (r % 8) * 64 + ((c ^ (r % 8)) * 8)      # element offsets (bytes / 2)
+        idx = off[:, None] + torch.arange(8)[None, :]
+        out[:, :, c * 8:(c + 1) * 8] = t[:, idx.reshape(-1)].reshape(ntiles, 128, 8)
+    return out.reshape(ntiles * 128, 64)[:rows, :F]
