@@ -109,7 +109,7 @@ SIGNATURES = {
     "durf_losses_prepare": (C.c_int, [_vp, C.POINTER(LossArgs), _vp]),
     "durf_losses_fwd_bwd": (C.c_int, [_vp, C.POINTER(LossArgs), _vp]),
     "durf_grad_sanitize": (C.c_int, [_vp, _i64, _vp, _f, _f, _vp]),
-    "durf_adam_step": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i32]),
+    "durf_adam_step": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f, _f, C.c_double, C.c_double, C.c_double, _i32]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -195,7 +195,7 @@ composite_bwd_kernel(const DurfCompositeArgs a, const float* __restrict__ d_comp
 static int check(const DurfCompositeArgs* a, const char* who) {
   DURF_REQUIRE(a != nullptr, DURF_E_INVALID, "%s: null args", who);
   DURF_REQUIRE(a->B >= 0 && a->N >= 1 && a->N <= 128, DURF_E_INVALID, "%s: need 1 <= N <= 128 (got %d)", who, a->N);
-  DURF_REQUIRE(a->raw_rgb && a->raw_density && a->t_vals && a->dirs, DURF_E_INVALID, "%s: null input", who);
+  DURF_REQUIRE(a->B == 0 || (a->raw_rgb && a->raw_density && a->t_vals && a->dirs), DURF_E_INVALID, "%s: null input", who);
   return DURF_OK;
 }
 
@@ -206,8 +206,8 @@ using namespace durf;
 extern "C" int durf_composite_fwd(durf_stream_t stream, const DurfCompositeArgs* args) {
   int rc = check(args, "durf_composite_fwd");
   if (rc != DURF_OK) return rc;
-  DURF_REQUIRE(args->comp_rgb && args->depth && args->acc && args->weights, DURF_E_INVALID, "durf_composite_fwd: null output");
   if (args->B == 0) return DURF_OK;
+  DURF_REQUIRE(args->comp_rgb && args->depth && args->acc && args->weights, DURF_E_INVALID, "durf_composite_fwd: null output");
   composite_fwd_kernel<<<ceil_div(args->B, 4), 128, 0, (cudaStream_t)stream>>>(*args);
   DURF_CHECK_LAUNCH("durf_composite_fwd");
   return DURF_OK;
@@ -218,9 +218,9 @@ extern "C" int durf_composite_bwd(durf_stream_t stream, const DurfCompositeArgs*
                                   float* d_raw_rgb, float* d_raw_density, float* d_dirs) {
   int rc = check(args, "durf_composite_bwd");
   if (rc != DURF_OK) return rc;
+  if (args->B == 0) return DURF_OK;
   DURF_REQUIRE(d_comp_rgb && d_depth && d_weights && d_raw_rgb && d_raw_density, DURF_E_INVALID,
                "durf_composite_bwd: null gradient buffer");
-  if (args->B == 0) return DURF_OK;
   composite_bwd_kernel<<<ceil_div(args->B, 4), 128, 0, (cudaStream_t)stream>>>(*args, d_comp_rgb, d_depth, d_acc, d_weights,
                                                                                 d_raw_rgb, d_raw_density, d_dirs);
   DURF_CHECK_LAUNCH("durf_composite_bwd");

@@ -172,7 +172,7 @@ static int check(const DurfLossArgs* a, const char* who) {
   DURF_REQUIRE(a->B >= 0 && a->N >= 1 && a->N <= 128, DURF_E_INVALID, "%s: need 1 <= N <= 128", who);
   DURF_REQUIRE(a->level >= 0 && a->level < a->num_levels && a->num_levels <= 2, DURF_E_INVALID, "%s: bad level %d/%d", who,
                a->level, a->num_levels);
-  DURF_REQUIRE(a->t_vals && a->depth_gt && a->sky && a->lossmult && a->dyn_mask && a->zo && a->depth_mask, DURF_E_INVALID,
+  DURF_REQUIRE(a->B == 0 || (a->t_vals && a->depth_gt && a->sky && a->lossmult && a->dyn_mask && a->zo && a->depth_mask), DURF_E_INVALID,
                "%s: null input", who);
   return DURF_OK;
 }
@@ -184,8 +184,8 @@ using namespace durf;
 extern "C" int durf_losses_prepare(durf_stream_t stream, const DurfLossArgs* args, float* norms) {
   int rc = check(args, "durf_losses_prepare");
   if (rc != DURF_OK) return rc;
-  DURF_REQUIRE(norms, DURF_E_INVALID, "durf_losses_prepare: null norms");
   if (args->B == 0) return DURF_OK;
+  DURF_REQUIRE(norms, DURF_E_INVALID, "durf_losses_prepare: null norms");
   losses_prepare_kernel<<<ceil_div(args->B, 4), 128, 0, (cudaStream_t)stream>>>(*args, norms);
   DURF_CHECK_LAUNCH("durf_losses_prepare");
   return DURF_OK;
@@ -194,6 +194,7 @@ extern "C" int durf_losses_prepare(durf_stream_t stream, const DurfLossArgs* arg
 extern "C" int durf_losses_fwd_bwd(durf_stream_t stream, const DurfLossArgs* args, const float* norms) {
   int rc = check(args, "durf_losses_fwd_bwd");
   if (rc != DURF_OK) return rc;
+  if (args->B == 0) return DURF_OK;
   DURF_REQUIRE(norms && args->comp_rgb && args->depth && args->weights && args->pixels && args->partials && args->d_comp_rgb &&
                    args->d_depth && args->d_weights, DURF_E_INVALID, "durf_losses_fwd_bwd: null buffer");
   if (args->B == 0) return DURF_OK;

@@ -250,6 +250,7 @@ extern "C" int durf_obb_frontend_fwd(durf_stream_t stream, int32_t B, int32_t K,
                                      float* zo_ret, float* nhit, float* origins_o, float* dirs_o) {
   DURF_REQUIRE(B >= 0 && K >= 1 && K <= kMaxObjects, DURF_E_INVALID,
                "durf_obb_frontend_fwd: need 1 <= K <= %d objects (got %d)", kMaxObjects, K);
+  if (B == 0) return DURF_OK;
   DURF_REQUIRE(origins && directions && box && ext && origins_s && dirs_s && hit && zi && zo && zo_ret && nhit,
                DURF_E_INVALID, "durf_obb_frontend_fwd: null argument");
   DURF_REQUIRE((origins_o == nullptr) == (dirs_o == nullptr), DURF_E_INVALID,
@@ -266,6 +267,7 @@ extern "C" int durf_obb_frontend_bwd(durf_stream_t stream, int32_t B, int32_t K,
                                      const float* d_origins_s, const float* d_dirs_s, int32_t pose_grad,
                                      int32_t rot_grad, float* d_box) {
   DURF_REQUIRE(B >= 0 && K >= 1 && K <= kMaxObjects, DURF_E_INVALID, "durf_obb_frontend_bwd: bad K=%d", K);
+  if (B == 0) return DURF_OK;
   DURF_REQUIRE(origins && directions && box && hit && d_origins_s && d_dirs_s && d_box, DURF_E_INVALID,
                "durf_obb_frontend_bwd: null argument");
   if (B == 0 || (!pose_grad && !rot_grad)) return DURF_OK;
@@ -277,7 +279,7 @@ extern "C" int durf_obb_frontend_bwd(durf_stream_t stream, int32_t B, int32_t K,
 
 extern "C" int durf_compact_hits(durf_stream_t stream, int32_t B, int32_t K, int32_t k, const int32_t* hit,
                                  int32_t* ray_index, int32_t* count) {
-  DURF_REQUIRE(B >= 0 && K >= 1 && k >= 0 && k < K && hit && ray_index && count, DURF_E_INVALID,
+  DURF_REQUIRE(B >= 0 && K >= 1 && k >= 0 && k < K && count && (B == 0 || (hit && ray_index)), DURF_E_INVALID,
                "durf_compact_hits: bad argument");
   cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int32_t), (cudaStream_t)stream);
   DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_compact_hits: memset: %s", cudaGetErrorString(e));

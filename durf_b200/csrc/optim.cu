@@ -30,13 +30,14 @@ grad_sanitize_kernel(int64_t n, float* __restrict__ g, float max_val, float scal
 
 __global__ void __launch_bounds__(256)
 adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            const float* __restrict__ sumsq, float max_norm, float lr, float b1, float b2, float eps, float c1, float c2) {
+            const float* __restrict__ sumsq, float max_norm, float lr, float b1, float b2, float omb1, float omb2, float eps,
+            float c1, float c2) {
   float mult = 1.f;
   if (max_norm > 0.f) mult = fminf(1.f, max_norm / (1e-7f + sqrtf(*sumsq)));   // train_boxpose.py:283-285
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = mult * g[i];
-    const float mi = (1.f - b1) * gi + b1 * m[i];
-    const float vi = (1.f - b2) * (gi * gi) + b2 * v[i];
+    const float mi = omb1 * gi + b1 * m[i];
+    const float vi = omb2 * (gi * gi) + b2 * v[i];
     m[i] = mi;
     v[i] = vi;
     const float mhat = mi / c1;
@@ -59,13 +60,15 @@ extern "C" int durf_grad_sanitize(durf_stream_t stream, int64_t n, float* grad, 
 }
 
 extern "C" int durf_adam_step(durf_stream_t stream, int64_t n, float* params, const float* grad, float* m, float* v,
-                              const float* sumsq, float max_norm, float lr, float beta1, float beta2, float eps, int32_t step) {
+                              const float* sumsq, float max_norm, float lr, double beta1, double beta2, double eps, int32_t step) {
   DURF_REQUIRE(n >= 0 && params && grad && m && v && sumsq && step >= 0, DURF_E_INVALID, "durf_adam_step: bad argument");
   if (n == 0) return DURF_OK;
   const double t = (double)step + 1.0;
-  const float c1 = (float)(1.0 - pow((double)beta1, t)), c2 = (float)(1.0 - pow((double)beta2, t));
+  const float c1 = (float)(1.0 - pow(beta1, t)), c2 = (float)(1.0 - pow(beta2, t));
+  // (1. - beta) is a Python double in flax.optim.Adam and only then meets the fp32 arrays
+  const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, params, grad, m, v, sumsq, max_norm, lr, beta1, beta2, eps, c1, c2);
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, params, grad, m, v, sumsq, max_norm, lr, (float)beta1, (float)beta2, omb1, omb2, (float)eps, c1, c2);
   DURF_CHECK_LAUNCH("durf_adam_step");
   return DURF_OK;
 }

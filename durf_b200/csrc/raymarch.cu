@@ -311,14 +311,15 @@ static int check_args(const DurfRaymarchArgs* a, RayMarchParams& p, const char* 
   const int D = a->max_deg - a->min_deg;
   DURF_REQUIRE(D >= 1 && D <= 16 && a->min_deg >= -60 && a->max_deg <= 60, DURF_E_INVALID, "%s: bad degree range [%d,%d)", who,
                a->min_deg, a->max_deg);
-  DURF_REQUIRE(a->origins && a->dirs && a->radii && a->t_vals && a->features, DURF_E_INVALID, "%s: null buffer", who);
-  if (a->flags & DURF_RM_SAMPLE) DURF_REQUIRE(a->near && a->far, DURF_E_INVALID, "%s: DURF_RM_SAMPLE needs near/far", who);
-  if (a->flags & DURF_RM_RANDOMIZED) DURF_REQUIRE(a->t_rand, DURF_E_INVALID, "%s: DURF_RM_RANDOMIZED needs t_rand", who);
-  DURF_REQUIRE((a->means == nullptr) == (a->cov_diag == nullptr), DURF_E_INVALID, "%s: means and cov_diag go together", who);
   p.a = *a;
   p.M = a->B;
   p.D = D;
   p.F = 6 * D + ((a->flags & DURF_RM_WEIGHTED) ? 3 : 0);
+  if (a->B == 0) return DURF_OK;     // empty batch: nothing is dereferenced, null buffers are fine
+  DURF_REQUIRE(a->origins && a->dirs && a->radii && a->t_vals && a->features, DURF_E_INVALID, "%s: null buffer", who);
+  if (a->flags & DURF_RM_SAMPLE) DURF_REQUIRE(a->near && a->far, DURF_E_INVALID, "%s: DURF_RM_SAMPLE needs near/far", who);
+  if (a->flags & DURF_RM_RANDOMIZED) DURF_REQUIRE(a->t_rand, DURF_E_INVALID, "%s: DURF_RM_RANDOMIZED needs t_rand", who);
+  DURF_REQUIRE((a->means == nullptr) == (a->cov_diag == nullptr), DURF_E_INVALID, "%s: means and cov_diag go together", who);
   if (a->flags & DURF_RM_OUT_BF16_TILE)
     DURF_REQUIRE(p.F <= 64 && 128 % a->N == 0, DURF_E_UNSUPPORTED, "%s: bf16 tile output needs F <= 64 and N | 128", who);
   return DURF_OK;
@@ -357,8 +358,9 @@ extern "C" int durf_raymarch_bwd(durf_stream_t stream, const DurfRaymarchArgs* a
 }
 
 extern "C" int durf_viewdir_enc_fwd(durf_stream_t stream, int32_t B, int32_t deg, const float* viewdirs, float* enc) {
-  DURF_REQUIRE(B >= 0 && deg >= 0 && deg <= 16 && viewdirs && enc, DURF_E_INVALID, "durf_viewdir_enc_fwd: bad argument");
+  DURF_REQUIRE(B >= 0 && deg >= 0 && deg <= 16, DURF_E_INVALID, "durf_viewdir_enc_fwd: bad argument");
   if (B == 0) return DURF_OK;
+  DURF_REQUIRE(viewdirs && enc, DURF_E_INVALID, "durf_viewdir_enc_fwd: null buffer");
   const int64_t total = (int64_t)B * (3 + 6 * deg);
   viewdir_enc_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(B, deg, viewdirs, enc);
   DURF_CHECK_LAUNCH("durf_viewdir_enc_fwd");

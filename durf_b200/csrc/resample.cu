@@ -107,8 +107,9 @@ extern "C" int durf_resample_fwd(durf_stream_t stream, int32_t B, int32_t N, con
                                  const float* u_rand, float resample_padding, int32_t blurpool, int32_t num_samples,
                                  float* new_t_vals) {
   DURF_REQUIRE(B >= 0 && N >= 1 && N <= 128, DURF_E_INVALID, "durf_resample_fwd: need 1 <= N <= 128 (got %d)", N);
-  DURF_REQUIRE(t_vals && weights && new_t_vals && num_samples >= 2, DURF_E_INVALID, "durf_resample_fwd: null buffer or num_samples < 2");
+  DURF_REQUIRE(num_samples >= 2, DURF_E_INVALID, "durf_resample_fwd: num_samples < 2");
   if (B == 0) return DURF_OK;
+  DURF_REQUIRE(t_vals && weights && new_t_vals, DURF_E_INVALID, "durf_resample_fwd: null buffer");
   ResampleParams p;
   p.B = B; p.N = N; p.S_out = num_samples; p.blur = blurpool; p.t_vals = t_vals; p.weights = weights; p.u_rand = u_rand; p.padding = blurpool ? resample_padding : 0.f;
   const double s = 1.0 / (double)num_samples;

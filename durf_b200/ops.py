@@ -17,6 +17,10 @@ BG_TOPOLOGY = (60, 256, 8, 4, 27, 128)    # MLP, configs/carla_dyn.gin:55-58
 BOX_TOPOLOGY = (63, 128, 8, 4, 27, 128)   # BoxMLP defaults, obbpose_model.py:360-363
 
 
+# bench.py sets PROFILE = {'mlp': []} to collect a CUDA-event pair around every durf_mlp_fwd launch (same stream).
+PROFILE: Optional[dict] = None
+
+
 def topology(t) -> MlpTopology:
     return t if isinstance(t, MlpTopology) else MlpTopology(*t)
 
@@ -203,7 +207,13 @@ def mlp_fwd(topo, features, cond, blob, *, M: int, N: int, precision=L.PREC_BF16
             ws = torch.empty(int(lib.durf_mlp_workspace_bytes(C.byref(t), precision, M, N, 0)) // 4, device=dev)
     a = _mlp_args(t, precision, M, N, features, f32(cond), f32(blob), packed, ray_index, count, accumulate, raw_rgb, raw_density,
                   saved, ws)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.durf_mlp_fwd(stream_ptr(), C.byref(a)), "durf_mlp_fwd")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE['mlp'].append((e0, e1))
     return raw_rgb, raw_density, saved
 
 

@@ -252,9 +252,10 @@ int durf_losses_fwd_bwd(durf_stream_t stream, const DurfLossArgs* args, const fl
 /* ---- KA: gradient post-processing + Adam (train_boxpose.py:262-288) --------------------------- */
 /* nan_to_num(posinf=0) -> clip to +-max_val -> sum of squares into sumsq[0] (caller zeroes). */
 int durf_grad_sanitize(durf_stream_t stream, int64_t n, float* grad, float max_val, float grad_scale, float* sumsq);
-/* mult = min(1, max_norm / (1e-7 + sqrt(sumsq))) applied on the fly, then flax.optim.Adam. */
+/* mult = min(1, max_norm / (1e-7 + sqrt(sumsq))) applied on the fly, then flax.optim.Adam.  beta1/beta2/eps are
+ * doubles because they are Python floats in the reference: (1. - beta) is formed in double before it meets fp32. */
 int durf_adam_step(durf_stream_t stream, int64_t n, float* params, const float* grad, float* m, float* v,
-                   const float* sumsq, float max_norm, float lr, float beta1, float beta2, float eps, int32_t step);
+                   const float* sumsq, float max_norm, float lr, double beta1, double beta2, double eps, int32_t step);
 
 #ifdef __cplusplus
 }

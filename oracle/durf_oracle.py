@@ -763,7 +763,7 @@ def adam_step(params: Sequence[Tensor], grads: Sequence[Tensor], m: Sequence[Ten
     outp, outm, outv = [], [], []
     for p, g, mi, vi in zip(params, grads, m, v):
         m2 = (1.0 - beta1) * g + beta1 * mi
-        v2 = (1.0 - beta2) * g * g + beta2 * vi
+        v2 = (1.0 - beta2) * (g * g) + beta2 * vi       # flax: (1. - beta2) * lax.square(grad)
         mhat = m2 / (1.0 - beta1 ** t)
         denom = torch.sqrt(v2 / (1.0 - beta2 ** t)) + eps
         outp.append(p - lr * mhat / denom); outm.append(m2); outv.append(v2)

@@ -83,3 +83,42 @@ def unswizzle_tiles(tiles: torch.Tensor, rows: int, F: int) -> torch.Tensor:
         idx = off[:, None] + torch.arange(8)[None, :]
         out[:, :, c * 8:(c + 1) * 8] = t[:, idx.reshape(-1)].reshape(ntiles, 128, 8)
     return out.reshape(ntiles * 128, 64)[:rows, :F]
+
+
+def sampler_pdf_cdf(bins, weights):
+    """fp64 restatement of the pdf/cdf construction of math.sorted_piecewise_constant_pdf (math.py:237-251)."""
+    w = weights.double().cpu()
+    ws = w.sum(-1, keepdim=True)
+    pad = torch.clamp(1e-5 - ws, min=0.0)
+    w = w + pad / w.shape[-1]
+    pdf = w / (ws + pad)
+    cdf = torch.cat([torch.zeros_like(pdf[..., :1]), torch.clamp(torch.cumsum(pdf[..., :-1], -1), max=1.0),
+                     torch.ones_like(pdf[..., :1])], -1)
+    return pdf, cdf
+
+
+def cdf_at(bins, cdf, t):
+    """Piecewise-linear CDF F(t) (fp64) of the histogram (bins, cdf) at positions t [..., S]."""
+    b = bins.double().cpu().contiguous()
+    t = t.double().cpu().contiguous()
+    j = torch.clamp(torch.searchsorted(b, t, right=True) - 1, 0, b.shape[-1] - 2)
+    b0, b1 = torch.gather(b, -1, j), torch.gather(b, -1, j + 1)
+    c0, c1 = torch.gather(cdf, -1, j), torch.gather(cdf, -1, j + 1)
+    frac = torch.where(b1 > b0, (t - b0) / torch.clamp(b1 - b0, min=1e-300), torch.zeros_like(t))
+    return c0 + torch.clamp(frac, 0.0, 1.0) * (c1 - c0)
+
+
+def assert_samples_close(got, want, bins, weights, what="sampler", pos_rtol=1e-5, cdf_ulps=64):
+    """Inverse-CDF samples are ill-conditioned in position where a bin holds little mass (a 1-ulp difference in the
+    fp32 cumsum moves a sample by ulp * width / mass), but well-conditioned in CDF space.  A sample passes if it agrees
+    in position (pos_rtol * max(|t|,1)) OR in CDF space (cdf_ulps * eps32): the summation order of the scan (warp scan
+    here, XLA's associative scan in the reference, sequential in the oracle) is the only thing that differs."""
+    _, cdf = sampler_pdf_cdf(bins, weights)
+    got64, want64 = got.double().cpu(), want.double().cpu()
+    pos_ok = (got64 - want64).abs() <= pos_rtol * torch.clamp(want64.abs(), min=1.0)
+    dF = (cdf_at(bins, cdf, got64) - cdf_at(bins, cdf, want64)).abs()
+    cdf_ok = dF <= cdf_ulps * 1.1920929e-07
+    bad = ~(pos_ok | cdf_ok)
+    assert not bool(bad.any()), (f"{what}: {int(bad.sum())}/{bad.numel()} samples differ in position and in CDF space; "
+                                 f"worst dF={float(dF[bad].max()):.3e}")
+    return float(pos_ok.double().mean())

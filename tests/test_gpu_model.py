@@ -136,14 +136,24 @@ def test_train_step_loss_and_gradients(pose_opt):
         assert abs(float(a.norm() / b.norm()) - 1.0) <= 1e-2, f"{name}: gradient norm ratio {float(a.norm() / b.norm()):.5f}"
     if pose_opt:
         o, n = v.slots['box_centers']
-        H.assert_close(g[o:o + n], want[o:o + n], rtol=1e-3, atol_scale=float(want[o:o + n].abs().max()), what="d box_centers")
-    # Adam (first step: p - lr * sign-ish), against the oracle's update on the oracle's gradient
-    gs, _ = O.postprocess_grads([want.float()], O.LossConfig(grad_max_val=0.0, grad_max_norm=0.0))
-    p2, _, _ = O.adam_step([before.cpu()], gs, [torch.zeros_like(gs[0])], [torch.zeros_like(gs[0])], step=0, lr=1e-3)
-    moved = (v.flat.cpu() - before.cpu())
-    ref_moved = (p2[0] - before.cpu())
-    big = want.abs() > 1e-6 * want.abs().max()            # tiny gradients: sign of m/sqrt(v) is rounding noise
-    assert float((moved[big] - ref_moved[big]).abs().max()) <= 2e-5
+        # The pose gradient runs through sin(2^l x) up to l = 9: compare with the fp64 oracle and require the kernel's
+        # error to be no worse than 4x the fp32 oracle's own rounding error (floor 1e-4 of the largest entry).
+        p64 = H.oracle_params(sc, torch.float64)
+        p64['box_centers'].requires_grad_(True)
+        ret64 = _oracle_forward(sc, 2, True, alpha, cfg, dtype=torch.float64, params=p64)
+        l64, _ = O.loss_fn(ret64, H.oracle_rays(sc, torch.float64), tg['pixels'].double(), tg['depth'].double(),
+                           tg['sky'].double(), eps=3.0)
+        g64 = torch.autograd.grad(l64, p64['box_centers'])[0].reshape(-1)
+        scale = float(g64.abs().max())
+        err_oracle32 = float((want[o:o + n] - g64).abs().max())
+        err_kernel = float((g[o:o + n] - g64).abs().max())
+        assert err_kernel <= max(4.0 * err_oracle32, 1e-4 * scale), \
+            f"d box_centers: kernel err {err_kernel:.3e} vs fp32-oracle err {err_oracle32:.3e} (scale {scale:.3e})"
+    # Adam on the kernel's own (post-processed) gradient: the first step is ~lr * g / (|g| + eps), which is
+    # ill-conditioned in g where |g| ~ eps, so the update is checked for the SAME gradient on both sides.
+    gk = st['grad'].cpu()
+    p2, _, _ = O.adam_step([before.cpu()], [gk], [torch.zeros_like(gk)], [torch.zeros_like(gk)], step=0, lr=1e-3)
+    H.assert_close(v.flat.cpu() - before.cpu(), p2[0] - before.cpu(), rtol=1e-4, atol_scale=1e-3, what="adam update")
 
 
 def test_grad_sanitize_and_adam_kernels():
@@ -163,4 +173,4 @@ def test_grad_sanitize_and_adam_kernels():
         ops.adam_step(p, g, m, v, sumsq, max_norm=0.05, lr=1e-2, step=step)
         gs, _ = O.postprocess_grads([want[0]], O.LossConfig(grad_max_val=0.0, grad_max_norm=0.05))
         pp, mm, vv = O.adam_step(pp, gs, mm, vv, step=step, lr=1e-2)
-    H.assert_close(p, pp[0], what="adam params"); H.assert_close(m, mm[0], what="adam m"); H.assert_close(v, vv[0], rtol=1e-5, atol_scale=1e-6, what="adam v")
+    H.assert_close(p, pp[0], what="adam params"); H.assert_close(m, mm[0], what="adam m"); H.assert_close(v, vv[0], rtol=1e-5, atol_scale=1e-9, what="adam v")
