@@ -28,6 +28,7 @@ int mlp_fp32_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_
 int64_t mlp_tc_packed_bytes(const DurfMlpTopology& t);
 int mlp_tc_pack(cudaStream_t st, const DurfMlpTopology& t, const float* params, void* packed);
 int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a);
+size_t mlp_tc_workspace_bytes(const DurfMlpTopology& t, int64_t M);
 
 }  // namespace durf
 
@@ -67,7 +68,7 @@ extern "C" size_t durf_mlp_workspace_bytes(const DurfMlpTopology* topo, int32_t 
   const int64_t R = (int64_t)M * N;
   if (precision == DURF_PREC_FP32)
     return sizeof(float) * (training ? mlp_fp32_bwd_floats(*topo, R) : mlp_fp32_infer_floats(*topo, R));
-  return 0;   // the tensor-core chain keeps everything on chip
+  return mlp_tc_workspace_bytes(*topo, M);   // per-tile view bias of the condition layer; everything else stays on chip
 }
 
 extern "C" size_t durf_mlp_saved_bytes(const DurfMlpTopology* topo, int32_t precision, int32_t M, int32_t N) {

@@ -1,42 +1,59 @@
 // K2 -- the radiance/density MLP as a fused tcgen05 GEMM chain (sm_100a), forward.
 // Replaces MLP.__call__ / BoxMLP.__call__ (obbpose_model.py:305-354, 369-418) for width 256 / 128, cond_width 128.
 //
-// One persistent CTA per SM works on PAIRS of 128-row tiles (one tile = the 128 samples of one ray-level), so
-// every 16 KB weight chunk pulled from L2 feeds 256 rows.  Per layer:
-//   TMA producer (warp 0)  : streams the pre-tiled, pre-swizzled bf16 weight image chunk by chunk
-//                            (cp.async.bulk -> mbarrier) through a ring of shared-memory stages;
-//   MMA issuer  (warp 1)   : one thread issues tcgen05.mma (M=128, N=128, K=16, bf16 x bf16 -> fp32) with the
-//                            tile's activations (A, K-major SWIZZLE_128B in shared memory) against the staged
-//                            weight chunk (B); accumulators live in TMEM (128 lanes x width columns per tile);
-//   feature loader (warp 2): bulk-copies the bf16 feature tile image written by the ray-march kernel;
-//   epilogue (warps 4-7 for tile 0, 8-11 for tile 1): tcgen05.ld the accumulators, + bias, ReLU, bf16 pack and
-//                            write the next layer's A operand in place; the last trunk layer also forms the density
-//                            head, the condition layer's epilogue adds the per-ray view term as a bias, forms the
-//                            rgb head and writes raw_rgb / raw_density.
-// The skip connection (obbpose_model.py:332-333) is a fifth K block taken from the still-resident input tile;
-// the view direction (constant along a ray) enters the condition layer as a per-tile fp32 bias
-// (b + W_view^T enc), so its 27 input columns never occupy tensor-core K.
+// One persistent CTA per SM; one tile = the 128 samples of one ray-level = UMMA M.  Everything between the input
+// features and the raw outputs stays on chip:
+//   * accumulators (fp32, 128 lanes x W columns) AND the activations live in TENSOR MEMORY: the epilogue packs
+//     relu(acc + bias) to bf16 and writes it back to TMEM with tcgen05.st, and the next layer's tcgen05.mma takes its
+//     A operand straight from TMEM (".ts" form).  Two activation buffers alternate by layer, so shared memory is free
+//     for a deep ring of weight chunks;
+//   * every layer is issued as two N-halves.  The epilogue of half 0 runs while the tensor core computes half 1, and
+//     the next layer starts on the K blocks produced by half 0 while the epilogue of half 1 is still running, so the
+//     tensor pipe only waits for an epilogue if that epilogue is slower than half a layer of MMAs.
+// Warp roles (384 threads): warp 0 = weight producer (cp.async.bulk of pre-tiled, pre-swizzled bf16 chunks into an
+// mbarrier ring), warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator + feature-tile loader, warp 3 = stage releaser,
+// warps 4-11 = epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter split the columns of a half).
+// The skip connection (obbpose_model.py:332-333) is an extra K block read from the still-resident input tile (smem,
+// ".ss" form); the view direction (constant along a ray) enters the condition layer as a per-tile fp32 bias
+// (b + W_view^T enc), so its 27 input columns never occupy tensor-core K; the density head (N=1) and the rgb head
+// (N=3) are dot products inside the epilogues.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "mlp_topology.h"
 
 namespace durf {
 
 constexpr int kTileM = 128;
-constexpr int kChunkBytes = 16384;    // 128 (n) x 64 (k) bf16, K-major SWIZZLE_128B
-constexpr int kMaxG = 16;
+constexpr int kInpBytes = 16384;      // input tile image: 128 rows x 64 bf16, K-major SWIZZLE_128B
+constexpr int kBlockBytes = 16384;    // one weight block: 128 (n) x 64 (k) bf16, K-major SWIZZLE_128B
+constexpr int kMaxG = 12;
+constexpr int kMaxStages = 8;
+constexpr int kMaxChunks = 48;
 
 struct LayerSched {
-  int n_halves;     // output columns / 128
-  int n_act_kb;     // 64-wide K blocks taken from the activation tile
+  int n_halves;     // output columns / (W/2)
+  int n_act_kb;     // 64-wide K blocks taken from the activation buffer (TMEM)
   int uses_inp;     // +1 K block from the input-feature tile (layer 0, skip layer)
   int kind;         // 0 relu->act, 1 relu->act + density head, 2 linear->act (bottleneck), 3 condition + rgb head + output
   int bias_off;     // offset (floats) of this layer's bias inside the parameter blob
   int last_inp_use; // 1 if no later layer of the tile reads the input-feature tile
 };
 
+// One use of a weight-ring stage: the K blocks of one (layer, N-half) that come from the activation buffer, or the
+// single K block that comes from the input-feature tile (layer 0, skip layer).
+struct ChunkSched {
+  int g, nh;        // layer, N-half
+  int nkb;          // 16 KB weight blocks in this chunk
+  int inp;          // 1: A operand = input-feature tile (shared memory), 0: activation buffer (TMEM)
+  int first, last;  // first / last chunk of (g, nh): overwrite the accumulator / commit acc_full[nh]
+  int block0;       // index of the chunk's first 16 KB block inside the packed weight image
+};
+
 struct TcParams {
   const uint8_t* feat;       // bf16 tile images, 16 KB per tile
   const float* cond;         // [B, cond_dim]
+  const float* vbias;        // [M, 128] per-tile bias of the condition layer (b + W_view^T enc), from cond_bias_kernel
   const float* params;       // fp32 blob
   const uint8_t* packed;     // weight image
   const int32_t* ray_index;
@@ -48,9 +65,11 @@ struct TcParams {
   int G;                     // GEMM layers per tile: depth + 2
   int depth;
   int cond_dim;
-  int chunks_per_pair;
+  int n_chunks;              // ring-stage uses per tile
   int off_wden, off_bden, off_wrgb, off_brgb, off_wview;
+  int trace;                 // DURF_TC_TRACE=1: block 0 prints where its MMA thread and one epilogue thread spent their cycles
   LayerSched sched[kMaxG];
+  ChunkSched chunks[kMaxChunks];
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -92,20 +111,35 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// Shared-memory matrix descriptors are passed as (lo, hi) words: hi is constant (SBO, version, swizzle), lo holds the
+// start address >> 4, so stepping through K blocks is a 32-bit add.
 // D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 inputs, fp32 accumulate)
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+// D[tmem] (+)= A[tmem] * B[smem]: A is 128 lanes (rows) x 8 columns of packed bf16 pairs per K=16 step
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -115,20 +149,62 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Ties the loaded registers to a point after tcgen05.wait::ld (volatile asms keep their order), so no consumer of
+// the asynchronous load can be scheduled above the wait.  Emits no instruction.
+__device__ __forceinline__ void tmem_ld_pin(uint32_t (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 16)
+    asm volatile("" : "+r"(v[i]), "+r"(v[i + 1]), "+r"(v[i + 2]), "+r"(v[i + 3]), "+r"(v[i + 4]), "+r"(v[i + 5]), "+r"(v[i + 6]),
+                      "+r"(v[i + 7]), "+r"(v[i + 8]), "+r"(v[i + 9]), "+r"(v[i + 10]), "+r"(v[i + 11]), "+r"(v[i + 12]),
+                      "+r"(v[i + 13]), "+r"(v[i + 14]), "+r"(v[i + 15]));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 16-byte load from shared memory by 32-bit shared address.  Not volatile and no memory clobber: the tables read
+// with it (biases, head weights) are written once before the role dispatch, so the compiler may batch and hoist them.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 r;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
 }
 
-// Shared-memory matrix descriptor, K-major, SWIZZLE_128B: start>>4 | LBO(=1, unused for swizzled K-major)<<16 |
-// SBO (1024 B between 8-row groups)>>4 <<32 | version 1 <<46 | layout 2 <<61   (cute::UMMA::SmemDescriptor).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
+// Same load for data that changes during the kernel (the per-ray view bias): volatile keeps it ordered with the
+// named barriers that publish it.
+__device__ __forceinline__ float4 lds128_volatile(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+  return r;
 }
+
+// packed fp32 add (FADD2) and fp32 pair -> bf16x2 conversions (lo = first argument)
+__device__ __forceinline__ float2 add2(float a0, float a1, float2 b) {
+  float2 a = make_float2(a0, a1), r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): lo = start>>4 | LBO(=1, unused for
+// swizzled K-major)<<16; hi = SBO (1024 B between 8-row groups)>>4 | version 1 <<14 | layout SWIZZLE_128B (2) <<29.
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=BF16 (1<<7, 1<<10), K-major both,
 // N>>3 at bit 17, M>>4 at bit 24.
 __host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
@@ -137,27 +213,32 @@ __host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
 
 template <int W>
 struct TcCfg {
-  static constexpr int KB = W / 64;                       // K blocks of the activation tile
-  static constexpr int STAGES = (W == 256) ? 3 : 4;
-  static constexpr int ACT_BYTES = kTileM * W * 2;
-  static constexpr int TMEM_COLS = 2 * W;                 // two tiles; power of two >= 32
+  static constexpr int NHALF = W / 128;                   // N-halves per trunk layer (every tcgen05.mma is M=128, N=128)
+  static constexpr int KB = W / 64;                       // 64-wide K blocks of an activation row
+  static constexpr int CPW = 64;                          // columns one epilogue warp owns inside a half
+  static constexpr int STAGE_BYTES = KB * kBlockBytes;    // one ring stage holds the weights of one (layer, N-half)
+  static constexpr int STAGES = (W == 256) ? 3 : 6;
+  static constexpr int TMEM_COLS = 2 * W;                 // W accumulator columns + 2 x W/2 activation columns
+  static constexpr int ACC_COL = 0;
+  static constexpr int ACT_COL = W;                       // buffer b at ACT_COL + b * W/2 (bf16 pairs)
+  static constexpr int MAX_BIAS_LAYERS = 10;              // trunk (depth <= 9) + bottleneck
   // shared memory map (bytes, from a 1024-aligned base)
-  static constexpr int OFF_ACT = 0;
-  static constexpr int OFF_INP = OFF_ACT + 2 * ACT_BYTES;
-  static constexpr int OFF_WST = OFF_INP + 2 * kChunkBytes;
-  static constexpr int OFF_BIAS = OFF_WST + STAGES * kChunkBytes;     // fp32 [kMaxBiasLayers][W] trunk + bottleneck
-  static constexpr int N_BIAS = 13 * W;                               // depth <= 12 trunk layers + bottleneck
-  static constexpr int OFF_WDEN = OFF_BIAS + N_BIAS * 4;              // fp32 [W]
+  static constexpr int OFF_INP = 0;
+  static constexpr int OFF_RING = OFF_INP + kInpBytes;
+  static constexpr int OFF_BIAS = OFF_RING + STAGES * STAGE_BYTES;    // fp32 [MAX_BIAS_LAYERS][W]
+  static constexpr int OFF_WDEN = OFF_BIAS + MAX_BIAS_LAYERS * W * 4; // fp32 [W]
   static constexpr int OFF_WRGB = OFF_WDEN + W * 4;                   // fp32 [3][128]
-  static constexpr int OFF_VBIAS = OFF_WRGB + 3 * 128 * 4;            // fp32 [2][128]
-  static constexpr int OFF_MISC = OFF_VBIAS + 2 * 128 * 4;            // head biases [4] + tmem ptr + barriers
-  static constexpr int MISC_BYTES = 256;
+  static constexpr int OFF_VBIAS = OFF_WRGB + 3 * 128 * 4;            // fp32 [128]
+  static constexpr int OFF_PART = OFF_VBIAS + 128 * 4;                // fp32 [4][128] partial density / rgb of the upper column warps
+  static constexpr int OFF_MISC = OFF_PART + 4 * 128 * 4;             // head biases [4] + tmem ptr + barriers
+  static constexpr int MISC_BYTES = 512;
   static constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;     // + alignment slack
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 template <int W>
 __global__ void __launch_bounds__(384, 1)
-mlp_tc_fwd_kernel(const TcParams p) {
+mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
   using C = TcCfg<W>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -168,23 +249,22 @@ mlp_tc_fwd_kernel(const TcParams p) {
   float* s_wden = reinterpret_cast<float*>(smem + C::OFF_WDEN);
   float* s_wrgb = reinterpret_cast<float*>(smem + C::OFF_WRGB);
   float* s_vbias = reinterpret_cast<float*>(smem + C::OFF_VBIAS);
+  float* s_part = reinterpret_cast<float*>(smem + C::OFF_PART);
   float* s_hb = reinterpret_cast<float*>(smem + C::OFF_MISC);             // [0]=b_den, [1..3]=b_rgb
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::OFF_MISC + 16);
   const uint32_t bar0 = sbase + C::OFF_MISC + 32;
   // barrier map (8 bytes each)
   auto bar_full = [&](int s) { return bar0 + 8 * s; };
-  auto bar_empty = [&](int s) { return bar0 + 8 * (4 + s); };
-  auto bar_inp_full = [&](int t) { return bar0 + 8 * (8 + t); };
-  auto bar_inp_empty = [&](int t) { return bar0 + 8 * (10 + t); };
-  auto bar_acc_full = [&](int t) { return bar0 + 8 * (12 + t); };
-  auto bar_act_ready = [&](int t) { return bar0 + 8 * (14 + t); };
+  auto bar_empty = [&](int s) { return bar0 + 8 * (kMaxStages + s); };
+  const uint32_t bar_inp_full = bar0 + 8 * (2 * kMaxStages), bar_inp_empty = bar0 + 8 * (2 * kMaxStages + 1);
+  auto bar_acc_full = [&](int h) { return bar0 + 8 * (2 * kMaxStages + 2 + h); };
+  auto bar_a_ready = [&](int h) { return bar0 + 8 * (2 * kMaxStages + 4 + h); };
+  static_assert(32 + 8 * (2 * kMaxStages + 6) <= C::MISC_BYTES, "barrier area");
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(bar_inp_full(t), 1); mbar_init(bar_inp_empty(t), 1);
-      mbar_init(bar_acc_full(t), 1); mbar_init(bar_act_ready(t), 128);
-    }
+    mbar_init(bar_inp_full, 1); mbar_init(bar_inp_empty, 1);
+    for (int h = 0; h < 2; ++h) { mbar_init(bar_acc_full(h), 1); mbar_init(bar_a_ready(h), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -206,17 +286,20 @@ mlp_tc_fwd_kernel(const TcParams p) {
   const uint32_t tmem_base = *s_tmem;
 
   const int num_tiles = p.count ? min(*p.count, p.M) : p.M;
-  const int num_pairs = (num_tiles + 1) / 2;
+  const int halves_last = p.sched[p.G - 1].n_halves;
 
   if (warp == 0) {
-    // ===== weight producer =====
+    // ===== weight producer: one ring stage per (layer, N-half [, input block]) chunk =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-        for (int c = 0; c < p.chunks_per_pair; ++c) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int c = 0; c < p.n_chunks; ++c) {
+          const ChunkSched ck = p.chunks[c];
           mbar_wait(bar_empty(stage), phase ^ 1);
-          mbar_arrive_expect_tx(bar_full(stage), kChunkBytes);
-          bulk_g2s(sbase + C::OFF_WST + stage * kChunkBytes, p.packed + (size_t)c * kChunkBytes, kChunkBytes, bar_full(stage));
+          mbar_arrive_expect_tx(bar_full(stage), ck.nkb * kBlockBytes);
+          for (int kb = 0; kb < ck.nkb; ++kb)
+            bulk_g2s(sbase + C::OFF_RING + stage * C::STAGE_BYTES + kb * kBlockBytes,
+                     p.packed + (size_t)(ck.block0 + kb) * kBlockBytes, kBlockBytes, bar_full(stage));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -226,149 +309,204 @@ mlp_tc_fwd_kernel(const TcParams p) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(128, 128);
+      constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);     // SBO | version | SWIZZLE_128B
       uint32_t stage = 0, phase = 0;
-      uint32_t act_par[2] = {1, 1}, inp_par[2] = {0, 0};
-      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-        const bool active[2] = {true, 2 * pair + 1 < num_tiles};
-        for (int g = 0; g < p.G; ++g) {
-          const LayerSched& L = p.sched[g];
-          const int nkb = L.n_act_kb + L.uses_inp;
-          for (int nh = 0; nh < L.n_halves; ++nh) {
-            for (int kc = 0; kc < nkb; ++kc) {
-              mbar_wait(bar_full(stage), phase);
-              tc_fence_after();
-              const uint32_t b_addr = sbase + C::OFF_WST + stage * kChunkBytes;
+      uint32_t ar_par[2] = {0, 0}, inp_par = 0;
+      int it = 0;
+      const bool tr = p.trace && blockIdx.x == 0;
+      long long t_full = 0, t_ready = 0, t_inp = 0, t_begin = clock64(), tq = 0;
+      const uint32_t inp_lo = ((sbase + C::OFF_INP) & 0x3FFFF) >> 4 | (1u << 16);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int c = 0; c < p.n_chunks; ++c) {
+          const ChunkSched ck = p.chunks[c];
+          const uint32_t d_addr = tmem_base + C::ACC_COL + ck.nh * 128;
+          if (c == 0) {
+            if (tr) tq = clock64();
+            mbar_wait(bar_inp_full, inp_par); inp_par ^= 1;
+            if (tr) { t_inp += clock64() - tq; tq = clock64(); }
+            if (it > 0)      // accumulators of the previous tile's last layer must have been drained
+              for (int h = 0; h < halves_last; ++h) { mbar_wait(bar_a_ready(h), ar_par[h]); ar_par[h] ^= 1; }
+            if (tr) t_ready += clock64() - tq;
+          }
+          if (tr) tq = clock64();
+          mbar_wait(bar_full(stage), phase);
+          if (tr) t_full += clock64() - tq;
+          tc_fence_after();
+          const uint32_t b_lo = (((sbase + C::OFF_RING + stage * C::STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+          if (!ck.inp) {
+            const uint32_t a_buf = tmem_base + C::ACT_COL + (ck.g & 1) * (W / 2);     // written by the epilogue of layer g-1
 #pragma unroll
-              for (int t = 0; t < 2; ++t) {
-                if (!active[t]) continue;
-                if (nh == 0 && kc == 0) {
-                  mbar_wait(bar_act_ready(t), act_par[t]); act_par[t] ^= 1;   // A operand written, accumulators drained
-                  if (g == 0) { mbar_wait(bar_inp_full(t), inp_par[t]); inp_par[t] ^= 1; }
+            for (int kb = 0; kb < C::KB; ++kb) {
+              if (kb < ck.nkb) {
+                if (ck.nh == 0 && (kb & 1) == 0) {   // first K block produced by half kb/2 of the previous layer's epilogue
+                  if (tr) tq = clock64();
+                  mbar_wait(bar_a_ready(kb >> 1), ar_par[kb >> 1]); ar_par[kb >> 1] ^= 1;
                   tc_fence_after();
+                  if (tr) t_ready += clock64() - tq;
                 }
-                const uint32_t a_addr = (kc < L.n_act_kb) ? sbase + C::OFF_ACT + t * C::ACT_BYTES + kc * kChunkBytes
-                                                          : sbase + C::OFF_INP + t * kChunkBytes;
-                const uint32_t d_addr = tmem_base + t * W + nh * 128;
 #pragma unroll
                 for (int k16 = 0; k16 < 4; ++k16)
-                  umma_bf16(d_addr, umma_desc_sw128(a_addr + k16 * 32), umma_desc_sw128(b_addr + k16 * 32), idesc,
-                            (kc > 0 || k16 > 0) ? 1u : 0u);
+                  umma_ts(d_addr, a_buf + kb * 32 + k16 * 8, b_lo + ((kb * kBlockBytes + k16 * 32) >> 4), desc_hi, idesc,
+                          (ck.first && kb == 0 && k16 == 0) ? 0u : 1u);
               }
-              tc_commit(bar_empty(stage));                                     // frees the weight stage when the MMAs retire
-              if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
+          } else {
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16)
+              umma_ss(d_addr, inp_lo + ((k16 * 32) >> 4), b_lo + ((k16 * 32) >> 4), desc_hi, idesc, (ck.first && k16 == 0) ? 0u : 1u);
           }
-          for (int t = 0; t < 2; ++t) {
-            if (!active[t]) continue;
-            if (L.last_inp_use) tc_commit(bar_inp_empty(t));
-            tc_commit(bar_acc_full(t));
-          }
+          if (ck.last) tc_commit(bar_acc_full(ck.nh));      // the epilogue releases the ring stage(s) and the input tile
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (tr) printf("durf mlp_tc trace: MMA thread: %d tiles, total %lld cyc; waiting weights %lld, epilogue(a_ready) %lld, features %lld\n",
+                     it, clock64() - t_begin, t_full, t_ready, t_inp);
     }
     __syncwarp();
   } else if (warp == 2) {
-    // ===== feature-tile loader =====
+    // ===== feature-tile loader: the next tile's features arrive while the layers after the skip layer run =====
     if (lane == 0) {
-      uint32_t par[2] = {0, 0};
-      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-        for (int t = 0; t < 2; ++t) {
-          const int tile = 2 * pair + t;
-          if (tile >= num_tiles) continue;
-          mbar_wait(bar_inp_empty(t), par[t] ^ 1);
-          mbar_arrive_expect_tx(bar_inp_full(t), kChunkBytes);
-          bulk_g2s(sbase + C::OFF_INP + t * kChunkBytes, p.feat + (size_t)tile * kChunkBytes, kChunkBytes, bar_inp_full(t));
-          par[t] ^= 1;
-        }
+      uint32_t par = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(bar_inp_empty, par ^ 1);
+        mbar_arrive_expect_tx(bar_inp_full, kInpBytes);
+        bulk_g2s(sbase + C::OFF_INP, p.feat + (size_t)tile * kInpBytes, kInpBytes, bar_inp_full);
+        par ^= 1;
       }
     }
     __syncwarp();
+  } else if (warp == 3) {
+    // ===== stage releaser: when the MMAs of (layer, half) have retired, their weight stage(s) and, after the skip
+    // layer, the input tile are free.  (A tcgen05.commit per stage on the issuing thread would cost it ~190 cycles.)
+    if (lane == 0) {
+      uint32_t af_par[2] = {0, 0}, rel_stage = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        for (int g = 0; g < p.G; ++g) {
+          const LayerSched& L = p.sched[g];
+          for (int h = 0; h < L.n_halves; ++h) {
+            mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
+            const int n_rel = (L.n_act_kb > 0 ? 1 : 0) + L.uses_inp;
+            for (int r = 0; r < n_rel; ++r) { mbar_arrive(bar_empty(rel_stage)); if (++rel_stage == C::STAGES) rel_stage = 0; }
+            if (L.last_inp_use && h == L.n_halves - 1) mbar_arrive(bar_inp_empty);
+          }
+        }
+    }
+    __syncwarp();
   } else if (warp >= 4) {
-    // ===== epilogue: warps 4-7 own tile 0, warps 8-11 own tile 1; thread = accumulator row = sample =====
-    const int t = (warp - 4) >> 2;
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    // ===== epilogue: thread = accumulator row = sample; warps q and q+4 share TMEM lane quarter q =====
+    const int q = warp & 3;
+    const int ch = (warp - 4) >> 2;               // which 64-column slice of a half this warp owns
     const int row = q * 32 + lane;
-    const int tid_in_tile = row;
-    uint8_t* act = smem + C::OFF_ACT + t * C::ACT_BYTES;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + t * W;
-    uint32_t acc_par = 0;
-    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-      const int tile = 2 * pair + t;
-      if (tile >= num_tiles) break;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t af_par[2] = {0, 0};
+    constexpr int NG = C::CPW / 32;               // 32-column groups per warp per half
+    const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 128;
+    long long e_acc = 0, e_ld = 0, e_math = 0, e_st = 0, e_begin = clock64(), eq = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int ray = p.ray_index ? p.ray_index[tile] : tile;
-      // per-ray bias of the condition layer: b + W_view^T enc(viewdir)   (obbpose_model.py:343-350)
-      {
-        const LayerSched& Lc = p.sched[p.G - 1];
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");   // previous tile's readers of s_vbias are done
-        float vb = p.params[Lc.bias_off + tid_in_tile];
-        const float* cv = p.cond + (size_t)ray * p.cond_dim;
-        for (int i = 0; i < p.cond_dim; ++i) vb = fmaf(cv[i], p.params[p.off_wview + i * 128 + tid_in_tile], vb);
-        s_vbias[t * 128 + tid_in_tile] = vb;
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
-      }
+      // per-ray bias of the condition layer (b + W_view^T enc(viewdir), obbpose_model.py:343-350), precomputed per tile
+      const float vb_mine = (ch == 0) ? p.vbias[(size_t)tile * 128 + row] : 0.f;    // consumed only at the last layer
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // previous tile's readers of s_vbias / s_part are done
+      if (ch == 0) s_vbias[row] = vb_mine;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       float den = 0.f;
+      float rgb[3] = {0.f, 0.f, 0.f};
       for (int g = 0; g < p.G; ++g) {
         const LayerSched& L = p.sched[g];
-        mbar_wait(bar_acc_full(t), acc_par); acc_par ^= 1;
-        tc_fence_after();
-        if (L.kind != 3) {
-          const float* sb = s_bias + g * W;
-#pragma unroll 1
-          for (int cb = 0; cb < W / 32; ++cb) {
-            uint32_t v[32];
-            tmem_ld32(t_lane + cb * 32, v);
+        const uint32_t o_buf = t_lane + C::ACT_COL + ((g + 1) & 1) * (W / 2);
+        for (int h = 0; h < L.n_halves; ++h) {
+          const int col0 = h * 128 + ch * C::CPW;
+          if (tr) eq = clock64();
+          mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
+          if (tr) { e_acc += clock64() - eq; eq = clock64(); }
+          tc_fence_after();
+          uint32_t v[NG][32];
+          tmem_ld32_issue(t_lane + C::ACC_COL + col0, v[0]);
+          if (L.kind != 3) {
+            // software pipeline over the two 32-column groups: the TMEM load of group 1 and the bias fetches run
+            // under the arithmetic of group 0 (TMEM reads are the epilogue's floor: 32 B/cycle per lane quarter)
+            const uint32_t sb = sbase + C::OFF_BIAS + (g * W + col0) * 4;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t wv[4];
+            for (int i = 0; i < NG; ++i) {
+              float4 b4[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int col = cb * 32 + j * 8 + 2 * e;
-                float a0 = __uint_as_float(v[j * 8 + 2 * e]) + sb[col];
-                float a1 = __uint_as_float(v[j * 8 + 2 * e + 1]) + sb[col + 1];
-                if (L.kind != 2) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                if (L.kind == 1) { den = fmaf(a0, s_wden[col], den); den = fmaf(a1, s_wden[col + 1], den); }
-                wv[e] = pack_bf16x2(a0, a1);
+              for (int j = 0; j < 8; ++j) b4[j] = lds128(sb + (i * 32 + 4 * j) * 4);
+              tmem_ld_wait();
+              tmem_ld_pin(v[i]);
+              if (i + 1 < NG) tmem_ld32_issue(t_lane + C::ACC_COL + col0 + (i + 1) * 32, v[i + 1]);
+              if (tr && i == 0) { e_ld += clock64() - eq; eq = clock64(); }
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 a = add2(__uint_as_float(v[i][4 * j]), __uint_as_float(v[i][4 * j + 1]), make_float2(b4[j].x, b4[j].y));
+                const float2 b = add2(__uint_as_float(v[i][4 * j + 2]), __uint_as_float(v[i][4 * j + 3]), make_float2(b4[j].z, b4[j].w));
+                if (L.kind == 0) {
+                  pk[2 * j] = cvt_bf16x2_relu(a.x, a.y);
+                  pk[2 * j + 1] = cvt_bf16x2_relu(b.x, b.y);
+                } else if (L.kind == 1) {
+                  const float4 w4 = lds128(sbase + C::OFF_WDEN + (col0 + i * 32 + 4 * j) * 4);
+                  const float r0 = fmaxf(a.x, 0.f), r1 = fmaxf(a.y, 0.f), r2 = fmaxf(b.x, 0.f), r3 = fmaxf(b.y, 0.f);
+                  den = fmaf(r0, w4.x, den); den = fmaf(r1, w4.y, den); den = fmaf(r2, w4.z, den); den = fmaf(r3, w4.w, den);
+                  pk[2 * j] = cvt_bf16x2(r0, r1);
+                  pk[2 * j + 1] = cvt_bf16x2(r2, r3);
+                } else {
+                  pk[2 * j] = cvt_bf16x2(a.x, a.y);
+                  pk[2 * j + 1] = cvt_bf16x2(b.x, b.y);
+                }
               }
-              const int col0 = cb * 32 + j * 8;
-              *reinterpret_cast<uint4*>(act + (col0 >> 6) * kChunkBytes + sw128_offset(row, (col0 & 63) >> 3)) =
-                  make_uint4(wv[0], wv[1], wv[2], wv[3]);
+              tmem_st16(o_buf + (col0 + i * 32) / 2, pk);
             }
-          }
-          tc_fence_before();
-          fence_async_smem();            // generic-proxy stores -> visible to the tensor core's async proxy
-          mbar_arrive(bar_act_ready(t));
-        } else {
-          // condition layer (128 columns): + per-ray bias, ReLU, rgb head, write raw outputs
-          float rgb[3] = {0.f, 0.f, 0.f};
-          const float* vb = s_vbias + t * 128;
-#pragma unroll 1
-          for (int cb = 0; cb < 4; ++cb) {
-            uint32_t v[32];
-            tmem_ld32(t_lane + cb * 32, v);
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int col = cb * 32 + e;
-              const float a = fmaxf(__uint_as_float(v[e]) + vb[col], 0.f);
-              rgb[0] = fmaf(a, s_wrgb[col], rgb[0]);
-              rgb[1] = fmaf(a, s_wrgb[128 + col], rgb[1]);
-              rgb[2] = fmaf(a, s_wrgb[256 + col], rgb[2]);
-            }
-          }
-          tc_fence_before();
-          mbar_arrive(bar_act_ready(t));   // tile finished: accumulators drained, activation buffer free
-          const size_t o = (size_t)ray * kTileM + row;
-          const float dv = den + s_hb[0];
-          if (p.accumulate) {
-            p.raw_density[o] += dv;
-            p.raw_rgb[o * 3 + 0] += rgb[0] + s_hb[1];
-            p.raw_rgb[o * 3 + 1] += rgb[1] + s_hb[2];
-            p.raw_rgb[o * 3 + 2] += rgb[2] + s_hb[3];
+            if (tr) { e_math += clock64() - eq; eq = clock64(); }
+            tmem_st_wait();
+            if (tr) e_st += clock64() - eq;
+            tc_fence_before();
+            mbar_arrive(bar_a_ready(h));   // half h of the next layer's A operand is in TMEM
           } else {
-            p.raw_density[o] = dv;
-            p.raw_rgb[o * 3 + 0] = rgb[0] + s_hb[1];
-            p.raw_rgb[o * 3 + 1] = rgb[1] + s_hb[2];
-            p.raw_rgb[o * 3 + 2] = rgb[2] + s_hb[3];
+            // condition layer: + per-ray bias, ReLU, partial rgb head over this warp's columns
+#pragma unroll
+            for (int i = 1; i < NG; ++i) tmem_ld32_issue(t_lane + C::ACC_COL + col0 + i * 32, v[i]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < NG; ++i) tmem_ld_pin(v[i]);
+            tc_fence_before();
+            mbar_arrive(bar_a_ready(h));   // accumulators drained: the next tile's first layer may overwrite them
+            const uint32_t svb = sbase + C::OFF_VBIAS + col0 * 4, swr = sbase + C::OFF_WRGB + col0 * 4;
+#pragma unroll
+            for (int i = 0; i < NG; ++i)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int c = i * 32 + 4 * j;
+                const float4 vb = lds128_volatile(svb + c * 4);   // rewritten per tile
+                const float4 w0 = lds128(swr + c * 4), w1 = lds128(swr + (128 + c) * 4), w2 = lds128(swr + (256 + c) * 4);
+                const float a0 = fmaxf(__uint_as_float(v[i][4 * j]) + vb.x, 0.f), a1 = fmaxf(__uint_as_float(v[i][4 * j + 1]) + vb.y, 0.f);
+                const float a2 = fmaxf(__uint_as_float(v[i][4 * j + 2]) + vb.z, 0.f), a3 = fmaxf(__uint_as_float(v[i][4 * j + 3]) + vb.w, 0.f);
+                rgb[0] = fmaf(a0, w0.x, rgb[0]); rgb[0] = fmaf(a1, w0.y, rgb[0]); rgb[0] = fmaf(a2, w0.z, rgb[0]); rgb[0] = fmaf(a3, w0.w, rgb[0]);
+                rgb[1] = fmaf(a0, w1.x, rgb[1]); rgb[1] = fmaf(a1, w1.y, rgb[1]); rgb[1] = fmaf(a2, w1.z, rgb[1]); rgb[1] = fmaf(a3, w1.w, rgb[1]);
+                rgb[2] = fmaf(a0, w2.x, rgb[2]); rgb[2] = fmaf(a1, w2.y, rgb[2]); rgb[2] = fmaf(a2, w2.z, rgb[2]); rgb[2] = fmaf(a3, w2.w, rgb[2]);
+              }
           }
+        }
+      }
+      if (tr && tile + (int)gridDim.x >= num_tiles)
+        printf("durf mlp_tc trace: epilogue thread: total %lld cyc; waiting acc_full %lld, tmem ld %lld, math+st issue %lld, st wait %lld\n",
+               clock64() - e_begin, e_acc, e_ld, e_math, e_st);
+      // combine the two column slices of every row and write the raw outputs
+      if (ch == 1) {
+        s_part[row] = den; s_part[128 + row] = rgb[0]; s_part[256 + row] = rgb[1]; s_part[384 + row] = rgb[2];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ch == 0) {
+        const size_t o = (size_t)ray * kTileM + row;
+        const float dv = den + s_part[row] + s_hb[0];
+        const float r0 = rgb[0] + s_part[128 + row] + s_hb[1];
+        const float r1 = rgb[1] + s_part[256 + row] + s_hb[2];
+        const float r2 = rgb[2] + s_part[384 + row] + s_hb[3];
+        if (p.accumulate) {
+          p.raw_density[o] += dv;
+          p.raw_rgb[o * 3 + 0] += r0; p.raw_rgb[o * 3 + 1] += r1; p.raw_rgb[o * 3 + 2] += r2;
+        } else {
+          p.raw_density[o] = dv;
+          p.raw_rgb[o * 3 + 0] = r0; p.raw_rgb[o * 3 + 1] = r1; p.raw_rgb[o * 3 + 2] = r2;
         }
       }
     }
@@ -381,20 +519,39 @@ mlp_tc_fwd_kernel(const TcParams p) {
   }
 }
 
+// Per-tile bias of the condition layer: vbias[m][j] = b_cond[j] + sum_i enc(viewdir of ray m)[i] * W_cond[width + i][j].
+// The view direction is constant along a ray, so these 27 input columns never occupy tensor-core K.
+__global__ void __launch_bounds__(128)
+cond_bias_kernel(int M, const int32_t* __restrict__ count, const int32_t* __restrict__ ray_index, const float* __restrict__ cond,
+                 int cond_dim, const float* __restrict__ w_view, const float* __restrict__ b_cond, float* __restrict__ vbias) {
+  __shared__ float s_w[64 * 128];
+  const int n = count ? min(*count, M) : M;
+  for (int i = threadIdx.x; i < cond_dim * 128; i += blockDim.x) s_w[i] = w_view[i];
+  __syncthreads();
+  const int j = threadIdx.x;
+  const float b = b_cond[j];
+  for (int m = blockIdx.x; m < n; m += gridDim.x) {
+    const float* cv = cond + (size_t)(ray_index ? ray_index[m] : m) * cond_dim;
+    float vb = b;
+    for (int i = 0; i < cond_dim; ++i) vb = fmaf(cv[i], s_w[i * 128 + j], vb);
+    vbias[(size_t)m * 128 + j] = vb;
+  }
+}
+
 // fp32 parameter blob -> bf16 weight image: for every GEMM layer, N half and K block (the order the kernel
-// consumes them) one 128x64 K-major SWIZZLE_128B chunk.  One thread per 16-byte piece.
+// consumes them) one 128 x 64 K-major SWIZZLE_128B block of 16 KB.  One thread per 16-byte piece.
+constexpr int kMaxBlocks = 192;
 struct PackParams {
   const float* params;
   uint8_t* packed;
-  int n_chunks;
-  int W, in_dim;
-  // per chunk: source kernel offset, its leading dimension (= out dim), first source row, rows available, first column
-  int w_off[160], ld[160], k_first[160], k_avail[160], n_first[160], n_avail[160];
+  int n_blocks;
+  // per block: source kernel offset, its leading dimension (= out dim), first source row, rows available, first column
+  int w_off[kMaxBlocks], ld[kMaxBlocks], k_first[kMaxBlocks], k_avail[kMaxBlocks], n_first[kMaxBlocks], n_avail[kMaxBlocks];
 };
 __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)p.n_chunks * 128 * 8) return;
-  const int chunk = (int)(i / 1024), r = (int)(i % 1024) / 8, c = (int)(i % 8);
+  if (i >= (int64_t)p.n_blocks * 1024) return;
+  const int blk = (int)(i / 1024), r = (int)(i % 1024) / 8, c = (int)(i % 8);
   uint32_t w[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -402,21 +559,22 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int k = c * 8 + 2 * e + h;
-      v[h] = (k < p.k_avail[chunk] && r < p.n_avail[chunk])
-                 ? p.params[p.w_off[chunk] + (size_t)(p.k_first[chunk] + k) * p.ld[chunk] + p.n_first[chunk] + r]
+      v[h] = (k < p.k_avail[blk] && r < p.n_avail[blk])
+                 ? p.params[p.w_off[blk] + (size_t)(p.k_first[blk] + k) * p.ld[blk] + p.n_first[blk] + r]
                  : 0.f;
     }
     w[e] = pack_bf16x2(v[0], v[1]);
   }
-  *reinterpret_cast<uint4*>(p.packed + (size_t)chunk * kChunkBytes + sw128_offset(r, c)) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(p.packed + (size_t)blk * kBlockBytes + sw128_offset(r, c)) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 static bool tc_supported(const DurfMlpTopology& t) {
-  return (t.width == 256 || t.width == 128) && t.cond_width == 128 && t.in_dim <= 64 && t.depth <= 12 && t.cond_dim <= 64 &&
-         !(((t.depth - 1) % t.skip == 0) && t.depth - 1 > 0);
+  return (t.width == 256 || t.width == 128) && t.cond_width == 128 && t.in_dim <= 64 && t.depth >= 2 && t.depth <= 9 &&
+         t.cond_dim <= 64 && !(((t.depth - 1) % t.skip == 0) && t.depth - 1 > 0);
 }
 
-// Builds the per-layer schedule shared by the pack kernel and the MLP kernel.
+// Builds the per-layer schedule and the flat list of ring-stage uses shared by the pack kernel and the MLP kernel.
+// Returns the number of 16 KB weight blocks.
 static int build_sched(const DurfMlpTopology& t, TcParams& P) {
   MlpLayout L(t);
   const int KB = t.width / 64;
@@ -424,7 +582,6 @@ static int build_sched(const DurfMlpTopology& t, TcParams& P) {
   P.G = t.depth + 2;
   P.depth = t.depth;
   P.cond_dim = t.cond_dim;
-  int chunks = 0;
   for (int g = 0; g < P.G; ++g) {
     LayerSched& s = P.sched[g];
     if (g < t.depth) {
@@ -438,41 +595,56 @@ static int build_sched(const DurfMlpTopology& t, TcParams& P) {
     } else if (g == t.depth) {       // bottleneck = Dense_{depth+1}
       s.n_halves = t.width / 128; s.n_act_kb = KB; s.uses_inp = 0; s.kind = 2; s.bias_off = (int)L.b_off[t.depth + 1];
     } else {                         // condition layer = Dense_{depth+2}
-      s.n_halves = 1; s.n_act_kb = KB; s.uses_inp = 0; s.kind = 3; s.bias_off = (int)L.b_off[t.depth + 2];
+      s.n_halves = t.cond_width / 128; s.n_act_kb = KB; s.uses_inp = 0; s.kind = 3; s.bias_off = (int)L.b_off[t.depth + 2];
     }
     s.last_inp_use = 0;
-    chunks += s.n_halves * (s.n_act_kb + s.uses_inp);
   }
   P.sched[last_inp].last_inp_use = 1;
-  P.chunks_per_pair = chunks;
+  int blocks = 0, nc = 0;
+  for (int g = 0; g < P.G; ++g) {
+    const LayerSched& s = P.sched[g];
+    for (int nh = 0; nh < s.n_halves; ++nh) {
+      const int parts = (s.n_act_kb > 0 ? 1 : 0) + s.uses_inp;
+      int part = 0;
+      if (s.n_act_kb > 0) {
+        P.chunks[nc++] = ChunkSched{g, nh, s.n_act_kb, 0, part == 0, part == parts - 1, blocks};
+        blocks += s.n_act_kb; ++part;
+      }
+      if (s.uses_inp) {
+        P.chunks[nc++] = ChunkSched{g, nh, 1, 1, part == 0, part == parts - 1, blocks};
+        blocks += 1; ++part;
+      }
+    }
+  }
+  P.n_chunks = nc;
   P.off_wden = (int)L.w_off[t.depth]; P.off_bden = (int)L.b_off[t.depth];
   P.off_wrgb = (int)L.w_off[t.depth + 3]; P.off_brgb = (int)L.b_off[t.depth + 3];
   P.off_wview = (int)L.w_off[t.depth + 2] + t.width * t.cond_width;
-  return chunks;
+  return blocks;
 }
 
 int64_t mlp_tc_packed_bytes(const DurfMlpTopology& t) {
   if (!tc_supported(t)) return 0;
   TcParams P;
-  return (int64_t)build_sched(t, P) * kChunkBytes;
+  return (int64_t)build_sched(t, P) * kBlockBytes;
 }
 
 int mlp_tc_pack(cudaStream_t st, const DurfMlpTopology& t, const float* params, void* packed) {
   DURF_REQUIRE(tc_supported(t), DURF_E_UNSUPPORTED,
-               "durf_mlp_pack_weights: tensor-core path needs width 128/256, cond_width 128, in_dim <= 64");
+               "durf_mlp_pack_weights: tensor-core path needs width 128/256, cond_width 128, in_dim <= 64, depth <= 9");
   TcParams P;
-  const int chunks = build_sched(t, P);
-  DURF_REQUIRE(chunks <= 160, DURF_E_UNSUPPORTED, "durf_mlp_pack_weights: too many weight chunks (%d)", chunks);
+  const int blocks = build_sched(t, P);
+  DURF_REQUIRE(blocks <= kMaxBlocks && P.n_chunks <= kMaxChunks, DURF_E_UNSUPPORTED, "durf_mlp_pack_weights: too many weight blocks (%d)", blocks);
   MlpLayout L(t);
   PackParams pp;
-  pp.params = params; pp.packed = (uint8_t*)packed; pp.n_chunks = chunks; pp.W = t.width; pp.in_dim = t.in_dim;
+  pp.params = params; pp.packed = (uint8_t*)packed; pp.n_blocks = blocks;
   int c = 0;
   for (int g = 0; g < P.G; ++g) {
     const LayerSched& s = P.sched[g];
     const int layer = (g < t.depth) ? g : (g == t.depth ? t.depth + 1 : t.depth + 2);
     const int n_out = L.out_dim[layer];
     for (int nh = 0; nh < s.n_halves; ++nh)
-      for (int kc = 0; kc < s.n_act_kb + s.uses_inp; ++kc, ++c) {
+      for (int kc = 0; kc < s.n_act_kb + s.uses_inp; ++kc, ++c) {     // same order as build_sched's block numbering
         pp.w_off[c] = (int)L.w_off[layer];
         pp.ld[c] = n_out;
         pp.n_first[c] = nh * 128;
@@ -481,29 +653,44 @@ int mlp_tc_pack(cudaStream_t st, const DurfMlpTopology& t, const float* params, 
         else { pp.k_first[c] = (g == 0) ? 0 : t.width; pp.k_avail[c] = t.in_dim; }   // input-feature block (skip rows follow the trunk rows)
       }
   }
-  const int64_t total = (int64_t)chunks * 1024;
+  const int64_t total = (int64_t)blocks * 1024;
   pack_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(pp);
   DURF_CHECK_LAUNCH("durf_mlp_pack_weights");
   return DURF_OK;
 }
 
+size_t mlp_tc_workspace_bytes(const DurfMlpTopology& t, int64_t M) { return tc_supported(t) ? (size_t)M * 128 * sizeof(float) : 0; }
+
 int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a) {
   const DurfMlpTopology& t = a.topo;
   DURF_REQUIRE(tc_supported(t), DURF_E_UNSUPPORTED,
-               "durf_mlp_fwd(bf16): tensor-core path needs width 128/256, cond_width 128, in_dim <= 64");
+               "durf_mlp_fwd(bf16): tensor-core path needs width 128/256, cond_width 128, in_dim <= 64, depth <= 9");
   DURF_REQUIRE(a.N == kTileM, DURF_E_UNSUPPORTED, "durf_mlp_fwd(bf16): needs 128 samples per ray (got %d)", a.N);
   DURF_REQUIRE(a.packed && a.params && a.features && a.cond, DURF_E_INVALID, "durf_mlp_fwd(bf16): null buffer");
   DURF_REQUIRE(a.saved == nullptr, DURF_E_UNSUPPORTED, "durf_mlp_fwd(bf16): activation saving is not available on this path");
+  const size_t need = mlp_tc_workspace_bytes(t, a.M);
+  DURF_REQUIRE(a.workspace && a.workspace_bytes >= need, DURF_E_WORKSPACE, "durf_mlp_fwd(bf16): workspace %zu < %zu bytes",
+               a.workspace_bytes, need);
   TcParams P;
   build_sched(t, P);
+  P.vbias = (const float*)a.workspace;
+  {
+    MlpLayout L(t);
+    const int grid_b = a.M < 148 * 8 ? a.M : 148 * 8;
+    cond_bias_kernel<<<grid_b, 128, 0, st>>>(a.M, a.count, a.ray_index, a.cond, t.cond_dim,
+                                             a.params + L.w_off[t.depth + 2] + (size_t)t.width * t.cond_width,
+                                             a.params + L.b_off[t.depth + 2], (float*)a.workspace);
+    DURF_CHECK_LAUNCH("durf_mlp_fwd(bf16): cond_bias");
+  }
   P.feat = (const uint8_t*)a.features; P.cond = a.cond; P.params = a.params; P.packed = (const uint8_t*)a.packed;
   P.ray_index = a.ray_index; P.count = a.count; P.M = a.M; P.accumulate = a.accumulate;
   P.raw_rgb = a.raw_rgb; P.raw_density = a.raw_density;
+  static const int trace_env = getenv("DURF_TC_TRACE") ? atoi(getenv("DURF_TC_TRACE")) : 0;
+  P.trace = trace_env;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int pairs = (a.M + 1) / 2;
-  const int grid = pairs < sms ? pairs : sms;
+  const int grid = a.M < sms ? a.M : sms;
   cudaError_t e;
   if (t.width == 256) {
     e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);

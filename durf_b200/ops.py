@@ -205,6 +205,8 @@ def mlp_fwd(topo, features, cond, blob, *, M: int, N: int, precision=L.PREC_BF16
             saved = torch.empty(int(lib.durf_mlp_saved_bytes(C.byref(t), precision, M, N)) // 4, device=dev)
         else:
             ws = torch.empty(int(lib.durf_mlp_workspace_bytes(C.byref(t), precision, M, N, 0)) // 4, device=dev)
+    else:
+        ws = torch.empty(max(int(lib.durf_mlp_workspace_bytes(C.byref(t), precision, M, N, 0)) // 4, 1), device=dev)
     a = _mlp_args(t, precision, M, N, features, f32(cond), f32(blob), packed, ray_index, count, accumulate, raw_rgb, raw_density,
                   saved, ws)
     if PROFILE is not None:
