@@ -12,6 +12,7 @@ import torch.distributed as dist
 
 from . import _lib as L
 from . import ops
+from . import parallel
 from .obbpose_model import MipNerfModel, Variables
 from .utils import Config
 
@@ -85,10 +86,9 @@ def train_step(model: MipNerfModel, config: Config, rng, state: TrainState, batc
         w = config.tv_loss_mult * (1.0 + 0.1 * (len(ret) - 1))
         if not model.no_pose_opt:
             v.view_of(d_flat, 'box_centers')[ts, :, :3] += 2.0 * w * (v.box_centers[ts, :, :3] - prev.reshape(-1, 3)[: v.K])
-    if world_size > 1:
-        dist.all_reduce(d_flat, op=dist.ReduceOp.SUM)                      # jax.lax.pmean(grad, 'batch'), :253
+    scale = parallel.allreduce_gradients(d_flat) if world_size > 1 else 1.0   # jax.lax.pmean(grad, 'batch'), :253
     sumsq = torch.zeros(1, device=d_flat.device)
-    ops.grad_sanitize(d_flat, config.grad_max_val, 1.0 / world_size, sumsq)
+    ops.grad_sanitize(d_flat, config.grad_max_val, scale, sumsq)
     ops.adam_step(v.flat, d_flat, state.m, state.v, sumsq, max_norm=config.grad_max_norm, lr=lr, step=state.step)
     v.mark_dirty()
     state.step += 1
