@@ -29,6 +29,11 @@ int64_t mlp_tc_packed_bytes(const DurfMlpTopology& t);
 int mlp_tc_pack(cudaStream_t st, const DurfMlpTopology& t, const float* params, void* packed);
 int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a);
 size_t mlp_tc_workspace_bytes(const DurfMlpTopology& t, int64_t M);
+bool mlp_tc_bwd_supported(const DurfMlpTopology& t);
+int mlp_tc_saved_blocks(const DurfMlpTopology& t);
+int64_t mlp_tc_packed_t_bytes(const DurfMlpTopology& t);
+int mlp_tc_pack_t(cudaStream_t st, const DurfMlpTopology& t, const float* params, void* packed_t);
+int mlp_tc_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density, float* d_params);
 
 }  // namespace durf
 
@@ -55,12 +60,14 @@ extern "C" int64_t durf_mlp_param_offset(const DurfMlpTopology* topo, int32_t la
 
 extern "C" int64_t durf_mlp_packed_bytes(const DurfMlpTopology* topo) {
   if (!topology_ok(topo)) { set_error("durf_mlp_packed_bytes: bad topology"); return DURF_E_INVALID; }
-  return mlp_tc_packed_bytes(*topo);
+  return mlp_tc_packed_bytes(*topo) + mlp_tc_packed_t_bytes(*topo);   // forward image, then the transposed image of dgrad
 }
 
 extern "C" int durf_mlp_pack_weights(durf_stream_t stream, const DurfMlpTopology* topo, const float* params, void* packed) {
   DURF_REQUIRE(topology_ok(topo) && params && packed, DURF_E_INVALID, "durf_mlp_pack_weights: bad argument");
-  return mlp_tc_pack((cudaStream_t)stream, *topo, params, packed);
+  int rc = mlp_tc_pack((cudaStream_t)stream, *topo, params, packed);
+  if (rc != DURF_OK || !mlp_tc_bwd_supported(*topo)) return rc;
+  return mlp_tc_pack_t((cudaStream_t)stream, *topo, params, (uint8_t*)packed + mlp_tc_packed_bytes(*topo));
 }
 
 extern "C" size_t durf_mlp_workspace_bytes(const DurfMlpTopology* topo, int32_t precision, int32_t M, int32_t N, int32_t training) {
@@ -68,13 +75,15 @@ extern "C" size_t durf_mlp_workspace_bytes(const DurfMlpTopology* topo, int32_t 
   const int64_t R = (int64_t)M * N;
   if (precision == DURF_PREC_FP32)
     return sizeof(float) * (training ? mlp_fp32_bwd_floats(*topo, R) : mlp_fp32_infer_floats(*topo, R));
-  return mlp_tc_workspace_bytes(*topo, M);   // per-tile view bias of the condition layer; everything else stays on chip
+  // inference / forward: per-tile view bias of the condition layer; backward: the dz tile records read by wgrad
+  if (training) return mlp_tc_bwd_supported(*topo) ? (size_t)M * mlp_tc_saved_blocks(*topo) * 16384 : 0;
+  return mlp_tc_workspace_bytes(*topo, M);
 }
 
 extern "C" size_t durf_mlp_saved_bytes(const DurfMlpTopology* topo, int32_t precision, int32_t M, int32_t N) {
   if (!topology_ok(topo) || M < 0 || N < 1) return 0;
   if (precision == DURF_PREC_FP32) return sizeof(float) * mlp_fp32_saved_floats(*topo, (int64_t)M * N);
-  return 0;
+  return mlp_tc_bwd_supported(*topo) ? (size_t)M * mlp_tc_saved_blocks(*topo) * 16384 : 0;
 }
 
 static int check_mlp(const DurfMlpArgs* a, const char* who) {
@@ -101,7 +110,9 @@ extern "C" int durf_mlp_bwd(durf_stream_t stream, const DurfMlpArgs* args, const
   if (rc != DURF_OK) return rc;
   DURF_REQUIRE(d_raw_rgb && d_raw_density && d_params, DURF_E_INVALID, "durf_mlp_bwd: null gradient buffer");
   if (args->M == 0) return DURF_OK;
-  DURF_REQUIRE(args->precision == DURF_PREC_FP32, DURF_E_UNSUPPORTED,
-               "durf_mlp_bwd: only the fp32 path has a backward pass in this build");
-  return mlp_fp32_backward((cudaStream_t)stream, *args, d_raw_rgb, d_raw_density, d_params, d_features);
+  if (args->precision == DURF_PREC_FP32)
+    return mlp_fp32_backward((cudaStream_t)stream, *args, d_raw_rgb, d_raw_density, d_params, d_features);
+  DURF_REQUIRE(d_features == nullptr, DURF_E_UNSUPPORTED,
+               "durf_mlp_bwd(bf16): no input gradient on the tensor-core path (use DURF_PREC_FP32 for the box-pose gradient)");
+  return mlp_tc_backward((cudaStream_t)stream, *args, d_raw_rgb, d_raw_density, d_params);
 }

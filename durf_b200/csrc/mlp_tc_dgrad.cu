@@ -1,0 +1,412 @@
+// K2 backward, data gradients as a fused tcgen05 GEMM chain (sm_100a): the reverse of mlp_tc.cu.
+// Per tile (the 128 samples of one ray-level), from dL/d raw_rgb [128,3] and dL/d raw_density [128]:
+//   prologue : dZ_cond = (d_rgb W_rgb^T) * [cond_act > 0]                              (CUDA cores, N = 3 head)
+//   stage 0  : dBott   = dZ_cond W_cond[:width]^T                                      (K = 128)
+//   stage 1  : dZ_last = (dBott W_bott^T + d_density (x) w_density) * [a_last > 0]
+//   stage 2+ : dZ_{g-1} = (dZ_g W_g[:width]^T) * [a_{g-1} > 0]      g = depth-1 .. 1
+// Same machinery as the forward: accumulators AND the bf16 dZ operands live in tensor memory (tcgen05.mma .ts), every
+// stage is issued as N-halves so the masking epilogue of one half overlaps the MMAs of the other, the transposed weight
+// image streams through a 3-stage ring of 64 KB chunks.  Every dZ (and dBott, dZ_cond) is also written to HBM as tile
+// images: they are the B operands of the weight-gradient kernel (mlp_tc_wgrad.cu).  The ReLU masks come from the
+// activations the forward pass saved.  No input gradient is produced (the background branch needs none: its samples
+// depend on no parameter; the object-pose path uses the fp32 kernels).
+#include "tc_common.cuh"
+#include "mlp_topology.h"
+
+namespace durf {
+
+constexpr int kDgMaxStages = 12;
+
+struct DgStage {
+  int n_halves;     // output columns / 128
+  int n_kb;         // 64-wide K blocks of the incoming dZ
+  int kind;         // 0: linear (dBott); 1: + density term, mask; 2: mask
+  int mask_slot;    // block offset (inside a saved tile record) of the activation whose sign masks this stage's output
+  int out_slot;     // block offset (inside a dz tile record) where this stage's output is stored
+  int block0;       // first 16 KB block of this stage inside the transposed weight image
+};
+
+struct DgParams {
+  const uint8_t* saved;      // forward activations (tile records of saved_blocks blocks)
+  uint8_t* dz;               // output: dz tile records (same record shape)
+  const uint8_t* packed_t;   // transposed weight image
+  const float* params;       // fp32 blob (density / rgb head weights)
+  const float* d_raw_rgb;    // [B,128,3]
+  const float* d_raw_density;// [B,128]
+  const int32_t* ray_index;
+  const int32_t* count;
+  int M, saved_blocks;
+  int n_stages;
+  int cond_slot;             // slot of the condition layer (its activation in `saved`, dZ_cond in `dz`)
+  int off_wden, off_wrgb;
+  int trace;
+  DgStage st[kDgMaxStages];
+};
+
+template <int W>
+struct DgCfg {
+  static constexpr int KB = W / 64;
+  static constexpr int STAGE_BYTES = KB * kBlockBytes;
+  static constexpr int STAGES = (W == 256) ? 3 : 6;
+  static constexpr int TMEM_COLS = 2 * W;
+  static constexpr int ACC_COL = 0;
+  static constexpr int ACT_COL = W;
+  static constexpr int OFF_RING = 0;
+  static constexpr int OFF_WDEN = OFF_RING + STAGES * STAGE_BYTES;    // fp32 [W]
+  static constexpr int OFF_WRGB = OFF_WDEN + W * 4;                   // fp32 [128][4] (rgb head kernel rows, padded)
+  static constexpr int OFF_MISC = OFF_WRGB + 128 * 4 * 4;
+  static constexpr int MISC_BYTES = 256;
+  static constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+// keep a packed bf16 pair where the matching activation halfwords are non-zero (ReLU outputs are +0 or positive)
+__device__ __forceinline__ uint32_t mask_pair(uint32_t packed, uint32_t act) {
+  const uint32_t m = ((act & 0xFFFFu) ? 0xFFFFu : 0u) | ((act & 0xFFFF0000u) ? 0xFFFF0000u : 0u);
+  return packed & m;
+}
+
+template <int W>
+__global__ void __launch_bounds__(384, 1)
+mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
+  using C = DgCfg<W>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_wden = reinterpret_cast<float*>(smem + C::OFF_WDEN);   // filled below, read with ld.shared
+  float* s_wrgb = reinterpret_cast<float*>(smem + C::OFF_WRGB);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::OFF_MISC);
+  const uint32_t bar0 = sbase + C::OFF_MISC + 16;
+  auto bar_full = [&](int s) { return bar0 + 8 * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8 * (8 + s); };
+  auto bar_acc_full = [&](int h) { return bar0 + 8 * (16 + h); };
+  auto bar_a_ready = [&](int h) { return bar0 + 8 * (18 + h); };
+  const uint32_t bar_p_ready = bar0 + 8 * 20;
+  static_assert(16 + 8 * 21 <= C::MISC_BYTES, "barrier area");
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int h = 0; h < 2; ++h) { mbar_init(bar_acc_full(h), 1); mbar_init(bar_a_ready(h), 256); }
+    mbar_init(bar_p_ready, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(C::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < W; i += blockDim.x) s_wden[i] = p.params[p.off_wden + i];
+  for (int i = threadIdx.x; i < 128 * 4; i += blockDim.x) s_wrgb[i] = (i & 3) < 3 ? p.params[p.off_wrgb + (i >> 2) * 3 + (i & 3)] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int num_tiles = p.count ? min(*p.count, p.M) : p.M;
+  const int last_halves = p.st[p.n_stages - 1].n_halves;
+
+  if (warp == 0) {
+    // ===== weight producer: one ring stage per (stage, N-half) =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        for (int s = 0; s < p.n_stages; ++s) {
+          const DgStage S = p.st[s];
+          for (int nh = 0; nh < S.n_halves; ++nh) {
+            mbar_wait(bar_empty(stage), phase ^ 1);
+            mbar_arrive_expect_tx(bar_full(stage), S.n_kb * kBlockBytes);
+            for (int kb = 0; kb < S.n_kb; ++kb)
+              bulk_g2s(sbase + C::OFF_RING + stage * C::STAGE_BYTES + kb * kBlockBytes,
+                       p.packed_t + (size_t)(S.block0 + nh * S.n_kb + kb) * kBlockBytes, kBlockBytes, bar_full(stage));
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(128, 128);
+      constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      uint32_t stage = 0, phase = 0, ar_par[2] = {0, 0}, pr_par = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it)
+        for (int s = 0; s < p.n_stages; ++s) {
+          const DgStage S = p.st[s];
+          const uint32_t a_buf = tmem_base + C::ACT_COL + (s & 1) * (W / 2);
+          for (int nh = 0; nh < S.n_halves; ++nh) {
+            const uint32_t d_addr = tmem_base + C::ACC_COL + nh * 128;
+            if (s == 0 && nh == 0) {
+              if (it > 0)      // accumulators of the previous tile's last stage must have been drained
+                for (int h = 0; h < last_halves; ++h) { mbar_wait(bar_a_ready(h), ar_par[h]); ar_par[h] ^= 1; }
+              mbar_wait(bar_p_ready, pr_par); pr_par ^= 1;           // dZ_cond is in TMEM
+              tc_fence_after();
+            }
+            mbar_wait(bar_full(stage), phase);
+            tc_fence_after();
+            const uint32_t b_lo = (((sbase + C::OFF_RING + stage * C::STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+#pragma unroll
+            for (int kb = 0; kb < C::KB; ++kb) {
+              if (kb < S.n_kb) {
+                if (s > 0 && nh == 0 && (kb & 1) == 0) {   // first K block produced by half kb/2 of the previous stage's epilogue
+                  mbar_wait(bar_a_ready(kb >> 1), ar_par[kb >> 1]); ar_par[kb >> 1] ^= 1;
+                  tc_fence_after();
+                }
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16)
+                  umma_ts(d_addr, a_buf + kb * 32 + k16 * 8, b_lo + ((kb * kBlockBytes + k16 * 32) >> 4), desc_hi, idesc,
+                          (kb == 0 && k16 == 0) ? 0u : 1u);
+              }
+            }
+            tc_commit(bar_acc_full(nh));
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ===== stage releaser =====
+    if (lane == 0) {
+      uint32_t af_par[2] = {0, 0}, rel_stage = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        for (int s = 0; s < p.n_stages; ++s)
+          for (int h = 0; h < p.st[s].n_halves; ++h) {
+            mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
+            mbar_arrive(bar_empty(rel_stage));
+            if (++rel_stage == C::STAGES) rel_stage = 0;
+          }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===== epilogue: thread = sample row; warps q and q+4 share TMEM lane quarter q and split a half's 128 columns =====
+    const int q = warp & 3, ch = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t af_par[2] = {0, 0};
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int ray = p.ray_index ? p.ray_index[tile] : tile;
+      const uint8_t* sv = p.saved + (size_t)tile * p.saved_blocks * kBlockBytes;
+      uint8_t* dzt = p.dz + (size_t)tile * p.saved_blocks * kBlockBytes;
+      // ---- prologue: dZ_cond[row, c] = (sum_j d_rgb[row, j] W_rgb[c, j]) * [cond_act[row, c] > 0], c in this warp's 64 columns
+      {
+        const float* g3 = p.d_raw_rgb + ((size_t)ray * kTileM + row) * 3;
+        const float g0 = g3[0], g1 = g3[1], g2 = g3[2];
+        const int c0 = ch * 64;                                   // columns [c0, c0 + 64) = block ch of the condition slot
+        const uint8_t* act = sv + (size_t)(p.cond_slot + ch) * kBlockBytes;
+        uint8_t* out = dzt + (size_t)(p.cond_slot + ch) * kBlockBytes;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            const uint4 a4 = *reinterpret_cast<const uint4*>(act + sw128_offset(row, i * 4 + c8));
+            const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c0 + i * 32 + c8 * 8 + 2 * e;
+              const float4 w0 = lds128_volatile(sbase + C::OFF_WRGB + c * 16), w1 = lds128_volatile(sbase + C::OFF_WRGB + (c + 1) * 16);
+              const float v0 = fmaf(g2, w0.z, fmaf(g1, w0.y, g0 * w0.x)), v1 = fmaf(g2, w1.z, fmaf(g1, w1.y, g0 * w1.x));
+              pk[c8 * 4 + e] = mask_pair(cvt_bf16x2(v0, v1), aw[e]);
+            }
+            *reinterpret_cast<uint4*>(out + sw128_offset(row, i * 4 + c8)) =
+                make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+          }
+          tmem_st16(t_lane + C::ACT_COL + (c0 + i * 32) / 2, pk);     // A operand of stage 0 = activation buffer 0
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_p_ready);
+      }
+      const float gden = p.d_raw_density[(size_t)ray * kTileM + row];
+      for (int s = 0; s < p.n_stages; ++s) {
+        const DgStage S = p.st[s];
+        const uint32_t o_buf = t_lane + C::ACT_COL + ((s + 1) & 1) * (W / 2);
+        const bool feeds_next = s + 1 < p.n_stages;
+        for (int h = 0; h < S.n_halves; ++h) {
+          const int col0 = h * 128 + ch * 64;
+          // the mask rows of this thread's 64 columns: one 128-byte line of the saved activation block
+          const uint8_t* act = sv + (size_t)(S.mask_slot + (col0 >> 6)) * kBlockBytes;
+          uint4 m4[4];
+          if (S.kind != 0) {
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) m4[c8] = *reinterpret_cast<const uint4*>(act + sw128_offset(row, c8));
+          }
+          mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
+          tc_fence_after();
+          uint8_t* out = dzt + (size_t)(S.out_slot + (col0 >> 6)) * kBlockBytes;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            uint32_t v[32];
+            tmem_ld32_issue(t_lane + C::ACC_COL + col0 + i * 32, v);
+            tmem_ld_wait();
+            tmem_ld_pin(v);
+            uint32_t pk[16];
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              const uint32_t aw[4] = {m4[c8].x, m4[c8].y, m4[c8].z, m4[c8].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float v0 = __uint_as_float(v[c8 * 8 + 2 * e]), v1 = __uint_as_float(v[c8 * 8 + 2 * e + 1]);
+                if (S.kind == 1) {
+                  const float2 wd = lds64(sbase + C::OFF_WDEN + (col0 + i * 32 + c8 * 8 + 2 * e) * 4);
+                  v0 = fmaf(gden, wd.x, v0); v1 = fmaf(gden, wd.y, v1);
+                }
+                uint32_t pr = cvt_bf16x2(v0, v1);
+                if (S.kind != 0) pr = mask_pair(pr, aw[e]);
+                pk[c8 * 4 + e] = pr;
+              }
+              *reinterpret_cast<uint4*>(out + sw128_offset(row, i * 4 + c8)) =
+                  make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+            }
+            if (i == 0 && S.kind != 0) {       // mask rows of the second 32-column group
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8) m4[c8] = *reinterpret_cast<const uint4*>(act + sw128_offset(row, 4 + c8));
+            }
+            if (feeds_next) tmem_st16(o_buf + (col0 + i * 32) / 2, pk);
+          }
+          if (feeds_next) tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(bar_a_ready(h));     // next stage's A operand half is in TMEM (last stage: accumulators drained)
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+// Transposed weight image: for every backward stage, N half and K block one 128 x 64 block with
+// block[r][k] = kernel[in = n_first + r][out = k_first + k] (the contraction runs over the forward layer's outputs).
+constexpr int kDgMaxBlocks = 192;
+struct PackTParams {
+  const float* params;
+  uint8_t* packed;
+  int n_blocks;
+  int w_off[kDgMaxBlocks], ld[kDgMaxBlocks], in_first[kDgMaxBlocks], out_first[kDgMaxBlocks], out_avail[kDgMaxBlocks];
+};
+__global__ void pack_weights_t_kernel(const __grid_constant__ PackTParams p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)p.n_blocks * 1024) return;
+  const int blk = (int)(i / 1024), r = (int)(i % 1024) / 8, c = (int)(i % 8);
+  const float* src = p.params + p.w_off[blk] + (size_t)(p.in_first[blk] + r) * p.ld[blk] + p.out_first[blk] + c * 8;
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int k = c * 8 + 2 * e;
+    w[e] = pack_bf16x2(k < p.out_avail[blk] ? src[2 * e] : 0.f, k + 1 < p.out_avail[blk] ? src[2 * e + 1] : 0.f);
+  }
+  *reinterpret_cast<uint4*>(p.packed + (size_t)blk * kBlockBytes + sw128_offset(r, c)) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+bool mlp_tc_bwd_supported(const DurfMlpTopology& t) {
+  return (t.width == 256 || t.width == 128) && t.cond_width == 128 && t.in_dim <= 64 && t.depth >= 2 && t.depth <= 9 &&
+         t.cond_dim <= 32 && !(((t.depth - 1) % t.skip == 0) && t.depth - 1 > 0);
+}
+
+int mlp_tc_saved_blocks(const DurfMlpTopology& t) { return (t.depth + 1) * (t.width / 64) + t.cond_width / 64; }
+
+// stage list + per-block source description; returns the number of blocks of the transposed image
+static int build_dg(const DurfMlpTopology& t, DgParams& P, PackTParams* pp) {
+  MlpLayout L(t);
+  const int KB = t.width / 64, NH = t.width / 128;
+  auto slot = [&](int g) { return g * KB; };
+  int ns = 0, blocks = 0;
+  auto add = [&](int layer, int n_kb, int kind, int mask_slot, int out_slot) {
+    DgStage& S = P.st[ns++];
+    S.n_halves = NH; S.n_kb = n_kb; S.kind = kind; S.mask_slot = mask_slot; S.out_slot = out_slot; S.block0 = blocks;
+    for (int nh = 0; nh < NH; ++nh)
+      for (int kb = 0; kb < n_kb; ++kb, ++blocks)
+        if (pp) {
+          pp->w_off[blocks] = (int)L.w_off[layer]; pp->ld[blocks] = L.out_dim[layer];
+          pp->in_first[blocks] = nh * 128; pp->out_first[blocks] = kb * 64;
+          pp->out_avail[blocks] = L.out_dim[layer] - kb * 64 < 64 ? L.out_dim[layer] - kb * 64 : 64;
+        }
+  };
+  // stage 0: dBott = dZ_cond W_cond[:width]^T   (contraction over the 128 condition outputs)
+  add(t.depth + 2, t.cond_width / 64, 0, 0, slot(t.depth));
+  // stage 1: dZ_{depth-1} = (dBott W_bott^T + d_den (x) w_den) * [a_{depth-1} > 0]
+  add(t.depth + 1, KB, 1, slot(t.depth - 1), slot(t.depth - 1));
+  // stages 2..: dZ_{g-1} = (dZ_g W_g[:width]^T) * [a_{g-1} > 0]
+  for (int g = t.depth - 1; g >= 1; --g) add(g, KB, 2, slot(g - 1), slot(g - 1));
+  P.n_stages = ns;
+  P.cond_slot = slot(t.depth + 1);
+  P.off_wden = (int)L.w_off[t.depth];
+  P.off_wrgb = (int)L.w_off[t.depth + 3];
+  return blocks;
+}
+
+int64_t mlp_tc_packed_t_bytes(const DurfMlpTopology& t) {
+  if (!mlp_tc_bwd_supported(t)) return 0;
+  DgParams P;
+  return (int64_t)build_dg(t, P, nullptr) * kBlockBytes;
+}
+
+int mlp_tc_pack_t(cudaStream_t st, const DurfMlpTopology& t, const float* params, void* packed_t) {
+  DURF_REQUIRE(mlp_tc_bwd_supported(t), DURF_E_UNSUPPORTED, "durf_mlp_pack_weights: no tensor-core backward for this topology");
+  DgParams P;
+  PackTParams pp;
+  const int blocks = build_dg(t, P, &pp);
+  DURF_REQUIRE(blocks <= kDgMaxBlocks, DURF_E_UNSUPPORTED, "durf_mlp_pack_weights: too many transposed blocks (%d)", blocks);
+  pp.params = params; pp.packed = (uint8_t*)packed_t; pp.n_blocks = blocks;
+  pack_weights_t_kernel<<<ceil_div((int64_t)blocks * 1024, 256), 256, 0, st>>>(pp);
+  DURF_CHECK_LAUNCH("durf_mlp_pack_weights(transposed)");
+  return DURF_OK;
+}
+
+int mlp_tc_dgrad_launch(cudaStream_t st, const DurfMlpTopology& t, const DgParams& base) {
+  DgParams P = base;
+  build_dg(t, P, nullptr);
+  P.saved_blocks = mlp_tc_saved_blocks(t);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = P.M < sms ? P.M : sms;
+  cudaError_t e;
+  if (t.width == 256) {
+    e = cudaFuncSetAttribute(mlp_tc_dgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DgCfg<256>::SMEM_BYTES);
+    DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_bwd(bf16): smem attribute: %s", cudaGetErrorString(e));
+    mlp_tc_dgrad_kernel<256><<<grid, 384, DgCfg<256>::SMEM_BYTES, st>>>(P);
+  } else {
+    e = cudaFuncSetAttribute(mlp_tc_dgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DgCfg<128>::SMEM_BYTES);
+    DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_bwd(bf16): smem attribute: %s", cudaGetErrorString(e));
+    mlp_tc_dgrad_kernel<128><<<grid, 384, DgCfg<128>::SMEM_BYTES, st>>>(P);
+  }
+  DURF_CHECK_LAUNCH("durf_mlp_bwd(bf16): dgrad");
+  return DURF_OK;
+}
+
+}  // namespace durf
+
+// ---- durf_mlp_bwd(DURF_PREC_BF16): dgrad chain, then the weight-gradient kernel ---------------------------------------
+namespace durf {
+
+struct WgradParams;
+int64_t mlp_tc_packed_bytes(const DurfMlpTopology& t);
+int mlp_tc_wgrad_run(cudaStream_t st, const DurfMlpTopology& t, const uint8_t* saved, const uint8_t* feat, const uint8_t* dz,
+                     const float* d_raw_rgb, const float* d_raw_density, const float* cond, const int32_t* ray_index,
+                     const int32_t* count, int M, float* d_params);
+
+int mlp_tc_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density, float* d_params) {
+  const DurfMlpTopology& t = a.topo;
+  DURF_REQUIRE(mlp_tc_bwd_supported(t), DURF_E_UNSUPPORTED, "durf_mlp_bwd(bf16): no tensor-core backward for this topology");
+  DURF_REQUIRE(a.N == kTileM, DURF_E_UNSUPPORTED, "durf_mlp_bwd(bf16): needs 128 samples per ray (got %d)", a.N);
+  DURF_REQUIRE(a.saved && a.packed && a.features, DURF_E_INVALID, "durf_mlp_bwd(bf16): needs saved activations, weight images, feature tiles");
+  const size_t need = (size_t)a.M * mlp_tc_saved_blocks(t) * kBlockBytes;
+  DURF_REQUIRE(a.workspace && a.workspace_bytes >= need, DURF_E_WORKSPACE, "durf_mlp_bwd(bf16): workspace %zu < %zu bytes",
+               a.workspace_bytes, need);
+  DgParams P{};
+  P.saved = (const uint8_t*)a.saved; P.dz = (uint8_t*)a.workspace;
+  P.packed_t = (const uint8_t*)a.packed + mlp_tc_packed_bytes(t);
+  P.params = a.params; P.d_raw_rgb = d_raw_rgb; P.d_raw_density = d_raw_density;
+  P.ray_index = a.ray_index; P.count = a.count; P.M = a.M; P.trace = 0;
+  int rc = mlp_tc_dgrad_launch(st, t, P);
+  if (rc != DURF_OK) return rc;
+  return mlp_tc_wgrad_run(st, t, (const uint8_t*)a.saved, (const uint8_t*)a.features, (const uint8_t*)a.workspace, d_raw_rgb,
+                          d_raw_density, a.cond, a.ray_index, a.count, a.M, d_params);
+}
+
+}  // namespace durf

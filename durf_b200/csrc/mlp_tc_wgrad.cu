@@ -1,0 +1,327 @@
+// K2 backward, weight gradients on the tensor cores (sm_100a): for every Dense layer of MLP / BoxMLP
+// (obbpose_model.py:326-353, 390-417 under jax.value_and_grad, train_boxpose.py:251)
+//     dW[in, out] += A^T dZ        db[out] += column sums of dZ
+// summed over all samples.  A (the layer's bf16 input activations, saved by the forward kernel) and dZ (the bf16
+// pre-activation gradients written by the dgrad kernel) live in HBM as per-tile block images: 128 samples x 64 features,
+// 128-byte rows, SWIZZLE_128B.  For wgrad the SAMPLE index is the contraction index, so the very same images are
+// MN-major tcgen05 operands (the 128-byte rows run along M / N, the 8-row groups along K): no transpose is ever made.
+//
+// One persistent CTA per SM owns a contiguous range of tiles and walks the list of jobs (one per weight matrix).
+// Per job the [in <= 256, out <= 256] fp32 accumulator sits in TMEM (<= 512 columns) while the CTA streams its tiles
+// through a 3-stage ring (64 samples of A and dZ per stage, cp.async.bulk + mbarrier); at the end of the job the
+// accumulator is added to the global gradient with fp32 reductions.  The kernel is HBM-bound (64 B/cycle/SM of operand
+// bytes at full tensor rate), so the narrow heads (density N=1, rgb N=3, the 27 view inputs of the condition layer) and
+// all bias gradients are computed by the otherwise idle warps from the stages already in shared memory.
+#include "tc_common.cuh"
+#include "mlp_topology.h"
+
+namespace durf {
+
+constexpr int kWgStages = 3;
+constexpr int kHalfBlock = 8192;          // 64 samples of one block image
+constexpr int kWgStageBytes = 8 * kHalfBlock;
+constexpr int kMaxJobs = 16;
+
+struct WgradJob {
+  int a_src;        // 0: saved activations, 1: input-feature tiles
+  int a_off;        // first block of A inside the tile record
+  int a_blocks;     // 64-feature blocks of A (1, 2 or 4)
+  int z_off;        // first block of dZ inside the dz tile record
+  int z_blocks;     // 64-column blocks of dZ (0 = no tensor-core work: rgb-head pseudo job)
+  int dw_off;       // float offset of kernel[k_first][0] inside the gradient blob
+  int ld;           // out dim of the kernel
+  int k_valid;      // valid input rows (60 / 63 for the input-feature block, else 64 * a_blocks)
+  int n_valid;      // valid output columns
+  int db_off;       // float offset of the bias gradient, -1: none (second K part of the skip layer)
+  int extra;        // 0 none; 1: density head (vec = d_raw_density); 2: rgb head (vec = d_raw_rgb); 3: view part of the condition layer
+  int ex_off;       // float offset of the extra's kernel gradient
+  int ex_b_off;     // float offset of the extra's bias gradient (-1: none)
+};
+
+struct WgradParams {
+  const uint8_t* saved;       // forward activations, saved_blocks blocks per tile
+  const uint8_t* feat;        // input-feature tiles, 1 block per tile
+  const uint8_t* dz;          // dgrad outputs, dz_blocks blocks per tile
+  int saved_blocks, dz_blocks;
+  const float* d_raw_rgb;     // [B,128,3]
+  const float* d_raw_density; // [B,128]
+  const float* cond;          // [B,cond_dim]
+  const int32_t* ray_index;
+  const int32_t* count;
+  int M, cond_dim;
+  float* d_params;
+  int n_jobs;
+  WgradJob jobs[kMaxJobs];
+};
+
+__device__ __forceinline__ void red_add(float* addr, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory"); }
+
+__global__ void __launch_bounds__(384, 1)
+mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int OFF_MISC = kWgStages * kWgStageBytes;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + OFF_MISC);
+  const uint32_t bar0 = sbase + OFF_MISC + 16;
+  auto bar_full = [&](int s) { return bar0 + 8 * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8 * (4 + s); };
+  const uint32_t bar_acc_done = bar0 + 8 * 8, bar_acc_free = bar0 + 8 * 9;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1 + 8); }   // MMA commit + 8 aux warps
+    mbar_init(bar_acc_done, 1); mbar_init(bar_acc_free, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int num_tiles = p.count ? min(*p.count, p.M) : p.M;
+  const int per = (num_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = min(num_tiles, (int)blockIdx.x * per), t_end = min(num_tiles, t_begin + per);
+  const int my_tiles = t_end - t_begin;
+
+  if (warp == 0) {
+    // ===== producer: per (job, tile, sample half) one stage: a_blocks + z_blocks half blocks of 8 KB =====
+    if (lane == 0 && my_tiles > 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int j = 0; j < p.n_jobs; ++j) {
+        const WgradJob jb = p.jobs[j];
+        const uint8_t* a_base = jb.a_src ? p.feat : p.saved;
+        const size_t a_stride = (size_t)(jb.a_src ? 1 : p.saved_blocks) * kBlockBytes;
+        for (int tile = t_begin; tile < t_end; ++tile)
+          for (int half = 0; half < 2; ++half) {
+            mbar_wait(bar_empty(stage), phase ^ 1);
+            mbar_arrive_expect_tx(bar_full(stage), (jb.a_blocks + jb.z_blocks) * kHalfBlock);
+            const uint32_t dst = sbase + stage * kWgStageBytes;
+            for (int b = 0; b < jb.a_blocks; ++b)
+              bulk_g2s(dst + b * kHalfBlock, a_base + (size_t)tile * a_stride + (size_t)(jb.a_off + b) * kBlockBytes + half * kHalfBlock,
+                       kHalfBlock, bar_full(stage));
+            for (int b = 0; b < jb.z_blocks; ++b)
+              bulk_g2s(dst + (4 + b) * kHalfBlock,
+                       p.dz + ((size_t)tile * p.dz_blocks + jb.z_off + b) * kBlockBytes + half * kHalfBlock, kHalfBlock, bar_full(stage));
+            if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+          }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer: D[features of A, columns of dZ] += A^T dZ over the 64 samples of a stage (4 x K=16) =====
+    if (lane == 0 && my_tiles > 0) {
+      constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      uint32_t stage = 0, phase = 0, free_par = 0;
+      for (int j = 0; j < p.n_jobs; ++j) {
+        const WgradJob jb = p.jobs[j];
+        if (jb.z_blocks > 0 && j > 0) { mbar_wait(bar_acc_free, free_par); free_par ^= 1; tc_fence_after(); }   // previous accumulator was read out
+        for (int tile = t_begin; tile < t_end; ++tile)
+          for (int half = 0; half < 2; ++half) {
+            mbar_wait(bar_full(stage), phase);
+            tc_fence_after();
+            if (jb.z_blocks > 0) {
+              const int m_tiles = jb.a_blocks > 2 ? 2 : 1;
+              const uint32_t a_lbo = jb.a_blocks >= 2 ? (uint32_t)(kHalfBlock >> 4) : 0u;    // a single block is read twice (rows 64..127 unused)
+              const uint32_t N = jb.z_blocks * 64;
+              const uint32_t idesc = umma_idesc_mn(128, (int)N);
+              const uint32_t st = sbase + stage * kWgStageBytes;
+              const uint32_t b_lo = (((st + 4 * kHalfBlock) & 0x3FFFF) >> 4) | ((uint32_t)(kHalfBlock >> 4) << 16);
+              for (int mt = 0; mt < m_tiles; ++mt) {
+                const uint32_t a_lo = (((st + mt * 2 * kHalfBlock) & 0x3FFFF) >> 4) | (a_lbo << 16);
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16)
+                  umma_ss(tmem_base + mt * N, a_lo + ((k16 * 2048) >> 4), b_lo + ((k16 * 2048) >> 4), desc_hi, idesc,
+                          (tile == t_begin && half == 0 && k16 == 0) ? 0u : 1u);
+              }
+            }
+            tc_commit(bar_empty(stage));
+            if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+          }
+        if (jb.z_blocks > 0) tc_commit(bar_acc_done);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===== auxiliary warps: bias / narrow-head gradients from the stages in shared memory, then the accumulator read-out =====
+    const int t = threadIdx.x - 128;              // 0..255: column of dZ (bias sums) or feature of A (narrow heads)
+    const int q = warp & 3, ch = (warp - 4) >> 2;
+    uint32_t stage = 0, phase = 0, done_par = 0;
+    if (my_tiles > 0)
+      for (int j = 0; j < p.n_jobs; ++j) {
+        const WgradJob jb = p.jobs[j];
+        float bsum = 0.f;                          // column sum of dZ[:, t]
+        float ex[3] = {0.f, 0.f, 0.f};             // narrow-head gradients of feature t
+        float exb[3] = {0.f, 0.f, 0.f};
+        float cv[32];                              // view part: d kernel[width + i][t]
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cv[i] = 0.f;
+        const int nvec = jb.extra == 1 ? 1 : (jb.extra == 2 ? 3 : 0);
+        for (int tile = t_begin; tile < t_end; ++tile) {
+          const int ray = p.ray_index ? p.ray_index[tile] : tile;
+          float tsum = 0.f;
+          for (int half = 0; half < 2; ++half) {
+            mbar_wait(bar_full(stage), phase);
+            const uint8_t* st = smem + stage * kWgStageBytes;
+            if (jb.db_off >= 0 || jb.extra == 3) {
+              if (t < jb.z_blocks * 64) {
+                const uint8_t* zb = st + (4 + (t >> 6)) * kHalfBlock + (t & 7) * 2;
+                const int c8 = (t & 63) >> 3;
+                float s = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < 64; ++r)
+                  s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(zb + (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4)));
+                tsum += s;
+              }
+            }
+            if (nvec > 0 && t < jb.a_blocks * 64) {
+              const uint8_t* ab = st + (t >> 6) * kHalfBlock + (t & 7) * 2;
+              const int c8 = (t & 63) >> 3;
+              const float* vec = (jb.extra == 1 ? p.d_raw_density + (size_t)ray * kTileM : p.d_raw_rgb + (size_t)ray * kTileM * 3) +
+                                 (size_t)half * 64 * nvec;
+              for (int r = 0; r < 64; ++r) {
+                const float a = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(ab + (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4)));
+                for (int jv = 0; jv < nvec; ++jv) {
+                  const float g = __ldg(vec + r * nvec + jv);
+                  ex[jv] = fmaf(a, g, ex[jv]);
+                  if (t == 0) exb[jv] += g;
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty(stage));
+            if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+          }
+          bsum += tsum;
+          if (jb.extra == 3 && t < 128) {
+            const float* ve = p.cond + (size_t)ray * p.cond_dim;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < p.cond_dim) cv[i] = fmaf(__ldg(ve + i), tsum, cv[i]);
+          }
+        }
+        // per-CTA partial sums -> global gradient
+        if (jb.db_off >= 0 && t < jb.n_valid) red_add(p.d_params + jb.db_off + t, bsum);
+        if (nvec > 0 && t < jb.a_blocks * 64) {
+          for (int jv = 0; jv < nvec; ++jv) red_add(p.d_params + jb.ex_off + t * nvec + jv, ex[jv]);
+          if (t == 0 && jb.ex_b_off >= 0)
+            for (int jv = 0; jv < nvec; ++jv) red_add(p.d_params + jb.ex_b_off + jv, exb[jv]);
+        }
+        if (jb.extra == 3 && t < 128) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < p.cond_dim) red_add(p.d_params + jb.ex_off + i * jb.ld + t, cv[i]);
+        }
+        // accumulator read-out: lane = input feature, columns = output features
+        if (jb.z_blocks > 0) {
+          mbar_wait(bar_acc_done, done_par); done_par ^= 1;
+          tc_fence_after();
+          const int m_tiles = jb.a_blocks > 2 ? 2 : 1;
+          const int N = jb.z_blocks * 64;
+          for (int mt = 0; mt < m_tiles; ++mt) {
+            const int m = mt * 128 + q * 32 + lane;               // input feature (row of the kernel)
+            for (int c0 = ch * (N / 2); c0 < (ch + 1) * (N / 2); c0 += 32) {
+              uint32_t v[32];
+              tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + mt * N + c0, v);
+              tmem_ld_wait();
+              tmem_ld_pin(v);
+              if (m < jb.k_valid) {
+                float* dst = p.d_params + jb.dw_off + (size_t)m * jb.ld + c0;
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                  if (c0 + e < jb.n_valid) red_add(dst + e, __uint_as_float(v[e]));
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(bar_acc_free);
+        }
+      }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 256 + 1024;
+
+// Builds the job list for a topology.  Tile records: saved activations = [layer g][W/64 blocks] for the depth+1 trunk /
+// bottleneck layers, then 2 blocks of the condition layer's activation; dz has the same record shape (dz of layer g at
+// the slot of its output activation).
+int mlp_tc_wgrad_launch(cudaStream_t st, const DurfMlpTopology& t, int saved_blocks, const WgradParams& base) {
+  MlpLayout L(t);
+  WgradParams P = base;
+  const int KB = t.width / 64, G = t.depth + 2;
+  int nj = 0;
+  auto slot = [&](int g) { return g * KB; };       // block offset of layer g's output inside a tile record
+  for (int g = 0; g < G; ++g) {
+    const int layer = (g < t.depth) ? g : (g == t.depth ? t.depth + 1 : t.depth + 2);
+    const bool skip_in = (g >= 1) && (g < t.depth) && ((g - 1) % t.skip == 0) && (g - 1 > 0);
+    const int n_out = L.out_dim[layer];
+    const int zb = n_out / 64;
+    WgradJob jb{};
+    jb.z_off = slot(g); jb.z_blocks = zb; jb.ld = n_out; jb.n_valid = n_out; jb.db_off = (int)L.b_off[layer];
+    jb.extra = 0; jb.ex_off = 0; jb.ex_b_off = -1;
+    if (g == 0) { jb.a_src = 1; jb.a_off = 0; jb.a_blocks = 1; jb.dw_off = (int)L.w_off[layer]; jb.k_valid = t.in_dim; }
+    else {
+      // input of trunk layer g / bottleneck = activation g-1 (bottleneck: the last trunk activation); condition layer = bottleneck output
+      const int src = (g == t.depth) ? t.depth - 1 : g - 1;
+      jb.a_src = 0; jb.a_off = slot(src); jb.a_blocks = KB; jb.dw_off = (int)L.w_off[layer]; jb.k_valid = t.width;
+    }
+    if (g == t.depth) {       // bottleneck job also carries the density head: both read the last trunk activation
+      jb.extra = 1; jb.ex_off = (int)L.w_off[t.depth]; jb.ex_b_off = (int)L.b_off[t.depth];
+    }
+    if (g == t.depth + 1) {   // condition layer: the view inputs' rows follow the `width` bottleneck rows
+      jb.extra = 3; jb.ex_off = (int)L.w_off[layer] + t.width * t.cond_width;
+    }
+    P.jobs[nj++] = jb;
+    if (skip_in) {            // second K part of the skip layer: the re-concatenated input features (rows width .. width+in_dim)
+      WgradJob js = jb;
+      js.a_src = 1; js.a_off = 0; js.a_blocks = 1; js.dw_off = (int)L.w_off[layer] + t.width * n_out; js.k_valid = t.in_dim;
+      js.db_off = -1; js.extra = 0;
+      P.jobs[nj++] = js;
+    }
+  }
+  {                           // rgb head: A = condition-layer activation, vec = d_raw_rgb; no tensor-core work
+    WgradJob jr{};
+    jr.a_src = 0; jr.a_off = slot(G - 1); jr.a_blocks = t.cond_width / 64; jr.z_blocks = 0; jr.db_off = -1;
+    jr.extra = 2; jr.ex_off = (int)L.w_off[t.depth + 3]; jr.ex_b_off = (int)L.b_off[t.depth + 3];
+    P.jobs[nj++] = jr;
+  }
+  DURF_REQUIRE(nj <= kMaxJobs, DURF_E_UNSUPPORTED, "durf_mlp_bwd(bf16): too many wgrad jobs (%d)", nj);
+  P.n_jobs = nj;
+  P.saved_blocks = saved_blocks; P.dz_blocks = saved_blocks;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = P.M < sms ? P.M : sms;
+  cudaError_t e = cudaFuncSetAttribute(mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
+  DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_bwd(bf16): smem attribute: %s", cudaGetErrorString(e));
+  mlp_tc_wgrad_kernel<<<grid, 384, kWgSmemBytes, st>>>(P);
+  DURF_CHECK_LAUNCH("durf_mlp_bwd(bf16): wgrad");
+  return DURF_OK;
+}
+
+}  // namespace durf
+
+namespace durf {
+
+int mlp_tc_saved_blocks(const DurfMlpTopology& t);
+
+int mlp_tc_wgrad_run(cudaStream_t st, const DurfMlpTopology& t, const uint8_t* saved, const uint8_t* feat, const uint8_t* dz,
+                     const float* d_raw_rgb, const float* d_raw_density, const float* cond, const int32_t* ray_index,
+                     const int32_t* count, int M, float* d_params) {
+  WgradParams P{};
+  P.saved = saved; P.feat = feat; P.dz = dz; P.d_raw_rgb = d_raw_rgb; P.d_raw_density = d_raw_density; P.cond = cond;
+  P.ray_index = ray_index; P.count = count; P.M = M; P.cond_dim = t.cond_dim; P.d_params = d_params;
+  return mlp_tc_wgrad_launch(st, t, mlp_tc_saved_blocks(t), P);
+}
+
+}  // namespace durf

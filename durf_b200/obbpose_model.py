@@ -94,8 +94,9 @@ class MipNerfModel:
         parameters live in `variables`, as `self.param('box_centers', ...)` does after initialisation).
         When `ctx` (a dict) is given the forward keeps what the backward pass needs in it."""
         prec = L.PREC_BF16 if self.precision == 'bf16' else L.PREC_FP32
-        if ctx is not None and prec != L.PREC_FP32:
-            raise L.DurfError("training (ctx != None) runs the MLPs in precision='fp32' in this build")
+        if ctx is not None and prec != L.PREC_FP32 and self.dynamics and not (self.no_pose_opt and self.no_yaw_opt):
+            raise L.DurfError("the box-pose gradient (no_pose_opt/no_yaw_opt = False) needs precision='fp32': the tensor-core "
+                              "backward produces no input gradient")
         N = self.num_samples
         origins, dirs = ops.f32(rays.origins), ops.f32(rays.directions)
         B = origins.shape[0]
@@ -118,8 +119,8 @@ class MipNerfModel:
             for k in range(K):
                 idx, cnt = ops.compact_hits(hit, k)
                 m_host = None
-                if prec == L.PREC_FP32:
-                    m_host = int(cnt.item())                                 # parity mode sizes its buffers exactly
+                if prec == L.PREC_FP32 or ctx is not None:
+                    m_host = int(cnt.item())                                 # parity / training size their buffers exactly
                 obj_lists.append((idx, cnt, m_host))
         bt, ot = self.bg_topology(), self.box_topology()
         bf16 = prec == L.PREC_BF16
@@ -160,7 +161,8 @@ class MipNerfModel:
                                                 count=None if m_host is not None else cnt, accumulate=True, raw_rgb=raw_rgb,
                                                 raw_density=raw_density, save=ctx is not None)
                     if lvl_ctx is not None:
-                        lvl_ctx['obj'].append(dict(feat=rmo['features'], saved=saved_o, rows=rows))
+                        lvl_ctx['obj'].append(dict(feat=rmo['features'], saved=saved_o, rows=rows,
+                                                   count=None if m_host is not None else cnt))
             if randomized and self.density_noise > 0:
                 raw_density = raw_density + self.density_noise * rb['density_noise'][i_level]   # obbpose_model.py:237-240
             comp = ops.composite(raw_rgb, raw_density, t_vals, dirs_s, white_bkgd=white_bkgd, rand_bkgd=rand_bkgd,
@@ -191,8 +193,9 @@ class MipNerfModel:
                                                      g['comp_rgb'], g['depth'], g['weights'], white_bkgd=ctx['white_bkgd'],
                                                      rand_bkgd=ctx['rand_bkgd'], density_bias=self.density_bias,
                                                      want_d_dirs=pose_opt)
+            prec = L.PREC_BF16 if self.precision == 'bf16' else L.PREC_FP32
             ops.mlp_bwd(bt, lvl['feat_bg'], viewenc, variables.blob('MLP_0'), lvl['saved_bg'], g_rgb, g_den,
-                        variables.blob_of(d_flat, 'MLP_0'), M=B, N=N)
+                        variables.blob_of(d_flat, 'MLP_0'), M=B, N=N, precision=prec, packed=variables.packed.get('MLP_0'))
             if pose_opt:
                 d_ds += g_dirs * (fe['nhit'] > 0).float()[:, None]            # only object rays carry pose-dependent dirs
             for k, o in enumerate(lvl['obj']):
@@ -201,7 +204,8 @@ class MipNerfModel:
                 idx = ctx['obj_lists'][k][0]
                 dfeat = ops.mlp_bwd(ot, o['feat'], viewenc, variables.blob(f'BoxMLP_{k}'), o['saved'], g_rgb, g_den,
                                     variables.blob_of(d_flat, f'BoxMLP_{k}'), M=o['rows'], N=N, ray_index=idx,
-                                    want_d_features=pose_opt)
+                                    want_d_features=pose_opt, precision=prec, packed=variables.packed.get(f'BoxMLP_{k}'),
+                                    count=o.get('count'))
                 if pose_opt:
                     go = torch.zeros(B, 3, device=d_flat.device)
                     gd = torch.zeros(B, 3, device=d_flat.device)

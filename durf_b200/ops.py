@@ -207,6 +207,8 @@ def mlp_fwd(topo, features, cond, blob, *, M: int, N: int, precision=L.PREC_BF16
             ws = torch.empty(int(lib.durf_mlp_workspace_bytes(C.byref(t), precision, M, N, 0)) // 4, device=dev)
     else:
         ws = torch.empty(max(int(lib.durf_mlp_workspace_bytes(C.byref(t), precision, M, N, 0)) // 4, 1), device=dev)
+        if save:      # training on the tensor-core path: every layer's bf16 activations as tile images
+            saved = torch.empty(max(int(lib.durf_mlp_saved_bytes(C.byref(t), precision, M, N)), 16), device=dev, dtype=torch.uint8)
     a = _mlp_args(t, precision, M, N, features, f32(cond), f32(blob), packed, ray_index, count, accumulate, raw_rgb, raw_density,
                   saved, ws)
     if PROFILE is not None:
@@ -220,14 +222,17 @@ def mlp_fwd(topo, features, cond, blob, *, M: int, N: int, precision=L.PREC_BF16
 
 
 def mlp_bwd(topo, features, cond, blob, saved, d_raw_rgb, d_raw_density, d_blob, *, M: int, N: int, ray_index=None,
-            want_d_features=False):
-    """Accumulates into d_blob; returns d_features [M*N, in_dim] or None."""
+            want_d_features=False, precision=L.PREC_FP32, packed=None, count=None):
+    """Accumulates into d_blob; returns d_features [M*N, in_dim] (fp32 path only) or None."""
     t = topology(topo)
     dev = _dev(features)
     lib = L.load()
-    ws = torch.empty(int(lib.durf_mlp_workspace_bytes(C.byref(t), L.PREC_FP32, M, N, 1)) // 4, device=dev)
+    nbytes = int(lib.durf_mlp_workspace_bytes(C.byref(t), precision, M, N, 1))
+    ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
+    if want_d_features and precision != L.PREC_FP32:
+        raise L.DurfError("the tensor-core backward produces no input gradient; use precision='fp32' for the box-pose gradient")
     dfeat = torch.empty(M * N, t.in_dim, device=dev) if want_d_features else None
-    a = _mlp_args(t, L.PREC_FP32, M, N, features, f32(cond), f32(blob), None, ray_index, None, False, d_raw_rgb, d_raw_density,
+    a = _mlp_args(t, precision, M, N, features, f32(cond), f32(blob), packed, ray_index, count, False, d_raw_rgb, d_raw_density,
                   saved, ws)
     check(lib.durf_mlp_bwd(stream_ptr(), C.byref(a), ptr(f32(d_raw_rgb)), ptr(f32(d_raw_density)), ptr(d_blob), ptr(dfeat)),
           "durf_mlp_bwd")

@@ -122,3 +122,40 @@ def assert_samples_close(got, want, bins, weights, what="sampler", pos_rtol=1e-5
     assert not bool(bad.any()), (f"{what}: {int(bad.sum())}/{bad.numel()} samples differ in position and in CDF space; "
                                  f"worst dF={float(dF[bad].max()):.3e}")
     return float(pos_ok.double().mean())
+
+
+def _bf16_ste(x):
+    """Round to bf16 in the forward pass, identity in the backward pass (straight-through)."""
+    return x + (x.to(torch.bfloat16).to(x.dtype) - x).detach()
+
+
+def mlp_apply_bf16_emulated(params, topo, x, condition):
+    """The oracle's MLP (oracle.mlp_apply, obbpose_model.py:305-354) with the tensor-core path's quantisation points made
+    explicit: GEMM operands (input features, trunk/bottleneck activations, kernels of the tensor-core layers) are rounded
+    to bf16, accumulation, biases, the density / rgb heads and the 27 view inputs stay fp32.  Test infrastructure: it
+    separates "bf16 arithmetic" from "kernel bug" when the CUDA gradients are compared (ReLU masks then agree)."""
+    B, N, F = x.shape
+    x = _bf16_ste(x.reshape(-1, F))
+    inputs = x
+    li = 0
+    q = _bf16_ste
+    h = x
+    for i in range(topo.depth):
+        k, b = params[li]; li += 1
+        pre = h @ q(k) + b
+        a = torch.relu(pre)
+        h_fp32 = a                     # the density head reads the fp32 ReLU output of the last trunk layer
+        h = q(a)
+        if i % topo.skip == 0 and i > 0:
+            h = torch.cat([h, inputs], dim=-1)
+    k, b = params[li]; li += 1
+    raw_density = (h_fp32 @ k + b).reshape(-1, N, 1)
+    k, b = params[li]; li += 1
+    bott = q(h @ q(k) + b)
+    k, b = params[li]; li += 1
+    W = topo.width
+    cond = condition[:, None, :].expand(B, N, condition.shape[-1]).reshape(-1, condition.shape[-1])
+    c = torch.relu(bott @ q(k[:W]) + cond @ k[W:] + b)
+    k, b = params[li]
+    raw_rgb = (c @ k + b).reshape(-1, N, 3)
+    return raw_rgb, raw_density

@@ -174,3 +174,43 @@ def test_grad_sanitize_and_adam_kernels():
         gs, _ = O.postprocess_grads([want[0]], O.LossConfig(grad_max_val=0.0, grad_max_norm=0.05))
         pp, mm, vv = O.adam_step(pp, gs, mm, vv, step=step, lr=1e-2)
     H.assert_close(p, pp[0], what="adam params"); H.assert_close(m, mm[0], what="adam m"); H.assert_close(v, vv[0], rtol=1e-5, atol_scale=1e-9, what="adam v")
+
+
+def test_train_step_tensor_core():
+    """C3 on the tensor-core path (precision='bf16': tcgen05 forward with saved activations, dgrad chain, wgrad kernel),
+    dynamic scene with two object MLPs on compacted rays: loss within 1e-2 of the fp32 oracle, every MLP's gradient
+    cosine >= 0.97 vs fp32 autograd (ReLU-mask flips of the bf16 forward, see test_mlp_tensor_core_backward), finite Adam."""
+    from durf_b200.train import TrainState, train_step
+    from durf_b200.utils import Config
+    sc = H.scene(B=384, K=2, seed=29)
+    cfg = O.ModelConfig()
+    params = H.oracle_params(sc)
+    leaves = [t for kb in params['mlp'] for t in kb] + [t for m in params['box_mlps'] for kb in m for t in kb]
+    for t in leaves:
+        t.requires_grad_(True)
+    ret = _oracle_forward(sc, 1, True, 10.0, cfg, params=params)
+    tg = {k: torch.from_numpy(v) for k, v in sc['targets'].items()}
+    loss, stats = O.loss_fn(ret, H.oracle_rays(sc), tg['pixels'], tg['depth'], tg['sky'], eps=3.0)
+    loss.backward()
+    model = _model(precision='bf16')
+    v = H.cuda_variables(sc, model)
+    state = TrainState.create(v)
+    batch = dict(rays=H.cuda_rays(sc), ext=torch.from_numpy(sc['ext']).cuda(), ts=torch.tensor([1]),
+                 pixels=tg['pixels'].cuda(), depth=tg['depth'].cuda(), sky=tg['sky'].cuda())
+    rng = dict(t_rand=torch.from_numpy(sc['t_rand']).cuda(), u_rand=torch.from_numpy(sc['u_rand']).cuda())
+    config = Config(grad_max_val=0.0, grad_max_norm=0.0)
+    state, st = train_step(model, config, rng, state, batch, lr=1e-3, eps=3.0, alpha=10.0)
+    assert abs(float(st['loss']) - float(loss)) <= 1e-2 * max(1.0, abs(float(loss))), (float(st['loss']), float(loss))
+    g = st['grad'].double().cpu()
+    want = H.flat_oracle_grads(sc, v, dict(
+        MLP_0=[(k.grad, b.grad) for k, b in params['mlp']],
+        **{f'BoxMLP_{i}': [(k.grad, b.grad) for k, b in m] for i, m in enumerate(params['box_mlps'])}))
+    assert torch.isfinite(g).all() and torch.isfinite(v.flat).all()
+    for name, (off, n) in v.slots.items():
+        a, b = g[off:off + n], want[off:off + n]
+        if float(b.norm()) == 0.0:
+            assert float(a.norm()) == 0.0, f"{name}: expected zero gradient"
+            continue
+        cos = float(a @ b / (a.norm() * b.norm()))
+        assert cos >= 0.97, f"{name}: gradient cosine {cos:.5f}"
+        assert abs(float(a.norm() / b.norm()) - 1.0) <= 0.1, f"{name}: gradient norm ratio {float(a.norm() / b.norm()):.4f}"
