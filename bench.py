@@ -183,6 +183,96 @@ def cpu_baseline(mlp, c2w, centers, ext_np):
                 sample=f"{n} random pixels of the same frame, one pass of oracle.model_forward ({dt:.1f} s), torch fp32 on {cores} threads")
 
 
+def train_bench(dev, rank, world, steps, warmup, precision):
+    """C3 (BASELINE.json configs[2]): one optimisation step on 16,384 rays per GPU -- dynamic scene (background + 2 object
+    NeRFs), mip360 contraction, stratified + hierarchical sampling with explicit random buffers, RGB + URF LIDAR depth /
+    line-of-sight (near, empty) + sky + distortion losses, backward, gradient mean over ranks (NCCL), clip, Adam.
+    Returns a dict for the "train" key of the JSON line (rays/s resident and end-to-end from pinned host batches)."""
+    import torch
+    import torch.distributed as dist
+    from durf_b200 import ops, synthetic as S
+    from durf_b200.obbpose_model import MipNerfModel, Variables
+    from durf_b200.train import TrainState, train_step
+    from durf_b200.utils import Config, Rays
+    B, K, N = 16384, 2, N_SAMPLES
+    rng = np.random.default_rng(S.SEED + 7 + rank)
+    rays_np, c2w = S.random_rays(rng, B, far=40.0)
+    centers, ext_np = S.boxes_in_view(rng, c2w, K)
+    rng_w = np.random.default_rng(S.SEED)                       # same weights on every rank
+    mlp = S.glorot_mlp(rng_w, 60, 256, 0.0)
+    box_mlps = [S.glorot_mlp(rng_w, 63, 128, 0.0) for _ in range(K)]
+    tg = S.targets(rng, B)
+    model = MipNerfModel(precision=precision, num_objects=K)
+    v = Variables.allocate(model, K, centers.shape[0], dev)
+    v.load_mlp("MLP_0", mlp)
+    for k, m in enumerate(box_mlps):
+        v.load_mlp(f"BoxMLP_{k}", m)
+    v.box_centers.copy_(torch.from_numpy(centers).to(dev))
+    v.mark_dirty()
+    state = TrainState.create(v)
+    config = Config()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    host = dict(rays=Rays(*[pin(a) for a in rays_np]), pixels=pin(tg['pixels']), depth=pin(tg['depth']), sky=pin(tg['sky']),
+                t_rand=pin(rng.uniform(size=(B, N + 1)).astype(np.float32)), u_rand=pin(rng.uniform(size=(B, N + 1)).astype(np.float32)))
+    ext = torch.from_numpy(ext_np).to(dev)
+    to_dev = lambda h: dict(rays=Rays(*[r.to(dev, non_blocking=True) for r in h['rays']]), ext=ext, ts=1,
+                            pixels=h['pixels'].to(dev, non_blocking=True), depth=h['depth'].to(dev, non_blocking=True),
+                            sky=h['sky'].to(dev, non_blocking=True))
+    resident = to_dev(host)
+    rnd_dev = dict(t_rand=host['t_rand'].to(dev), u_rand=host['u_rand'].to(dev))
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step_resident():
+        nonlocal state
+        state, st = train_step(model, config, rnd_dev, state, resident, lr=5e-4, eps=3.0, alpha=10.0, world_size=world)
+        return st
+
+    def step_e2e():
+        nonlocal state
+        batch = to_dev(host)
+        rnd = dict(t_rand=host['t_rand'].to(dev, non_blocking=True), u_rand=host['u_rand'].to(dev, non_blocking=True))
+        state, st = train_step(model, config, rnd, state, batch, lr=5e-4, eps=3.0, alpha=10.0, world_size=world)
+        loss_host.copy_(st['loss'].reshape(1), non_blocking=True)
+        return st
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / k
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    for _ in range(warmup):
+        st = step_resident()
+    ops.reset_launch_count()
+    ms = timed(step_resident, steps)
+    launches = ops.launch_count()
+    step_e2e()
+    ms_e2e = timed(step_e2e, steps)
+    loss = float(st['loss'])
+    h2d = sum(r.numel() * 4 for r in host['rays']) + sum(host[k].numel() * 4 for k in ('pixels', 'depth', 'sky', 't_rand', 'u_rand'))
+    # algorithmic MLP FLOPs of a step: fwd + dgrad + wgrad of the background MLP on every sample (object MLPs on hit rays are extra)
+    flops = 3.0 * B * 2 * N * MLP_FLOP_PER_SAMPLE
+    return dict(metric="rays/sec (train step, 2x128 samples)", value=B * world / (ms * 1e-3), unit="rays/s", ms_per_step=ms,
+                rays_per_step_per_gpu=B, steps=steps, warmup=warmup, dtype="bf16" if precision == "bf16" else "f32",
+                config="C3: 16384 rays/GPU, background + 2 object NeRFs, contraction, randomized sampling (explicit buffers), "
+                       "RGB + LIDAR depth/near/empty + sky + distortion losses, grad mean over ranks, clip, Adam",
+                e2e=dict(value=B * world / (ms_e2e * 1e-3), unit="rays/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
+                gpu_launches=int(launches), loss=loss, bg_mlp_tflops_algorithmic=flops / (ms * 1e-3) / 1e12)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,6 +283,9 @@ def main():
     ap.add_argument("--rows", type=int, default=H_FRAME, help="image rows per frame (default: the full 1280)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-train", action="store_true", help="skip the C3 train-step measurement")
+    ap.add_argument("--train-only", action="store_true", help="profiling aid: only the C3 train step (prints its dict)")
+    ap.add_argument("--train-steps", type=int, default=5)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -219,6 +312,13 @@ def main():
     from durf_b200.utils import Rays
     L.load()                                             # raises if libdurf_b200.so is missing
 
+    if args.train_only:
+        t = train_bench(dev, rank, world, args.train_steps, 3, args.precision)
+        if rank == 0:
+            print(json.dumps(t), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     mlp, c2w, centers, ext_np = frame_scene(rank)
     model = MipNerfModel(dynamics=False, contraction=True, num_objects=1, precision=args.precision)
     v = Variables.allocate(model, 1, 5, dev)
@@ -297,6 +397,12 @@ def main():
     frame_e2e()                                           # warm the e2e path (pinned staging, allocator)
     ms_e2e = timed(frame_e2e, steps)
 
+    train = None
+    if not args.no_train:
+        del dev_rays, out_rgb, out_dist, out_acc
+        torch.cuda.empty_cache()
+        train = train_bench(dev, rank, world, args.train_steps, 3, args.precision)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -323,6 +429,8 @@ def main():
                 e2e=dict(value=e2e_v, unit="rays/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e,
                          api="durf_b200.obbpose_model.render_image (pinned host rays -> pinned host rgb/distance/acc)"),
                 gpu_launches=int(launches), roofline=roof)
+    if train is not None:
+        line["train"] = train
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(mlp, c2w, centers, ext_np)
     print(json.dumps(line), flush=True)

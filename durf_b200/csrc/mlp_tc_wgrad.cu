@@ -147,68 +147,102 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===== auxiliary warps: bias / narrow-head gradients from the stages in shared memory, then the accumulator read-out =====
-    const int t = threadIdx.x - 128;              // 0..255: column of dZ (bias sums) or feature of A (narrow heads)
+    // ===== auxiliary warps: bias / narrow-head gradients from the stages in shared memory, then the accumulator read-out.
+    // Thread (rg, ck) of the 256 owns the 16-byte piece ck (8 consecutive columns) of the rows rg, rg+8, ... of a stage, so
+    // a stage costs it 8 ld.shared.v4 per operand; the 8 row groups of a column meet in the final reductions.
+    const int t = threadIdx.x - 128;
     const int q = warp & 3, ch = (warp - 4) >> 2;
+    const int ck = t & 31, rg = t >> 5;           // piece (0..31: block ck>>3, 16-byte chunk ck&7) and row group (0..7)
+    float* s_cs = reinterpret_cast<float*>(smem + OFF_MISC + 128);     // [8][128] per-tile column sums (view part)
     uint32_t stage = 0, phase = 0, done_par = 0;
     if (my_tiles > 0)
       for (int j = 0; j < p.n_jobs; ++j) {
         const WgradJob jb = p.jobs[j];
-        float bsum = 0.f;                          // column sum of dZ[:, t]
-        float ex[3] = {0.f, 0.f, 0.f};             // narrow-head gradients of feature t
-        float exb[3] = {0.f, 0.f, 0.f};
-        float cv[32];                              // view part: d kernel[width + i][t]
+        float bsum[8], ex[8][3], exb[3] = {0.f, 0.f, 0.f};
+        float cv[32];                              // view part: d kernel[width + i][t], threads t < 128
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { bsum[e] = 0.f; ex[e][0] = ex[e][1] = ex[e][2] = 0.f; }
 #pragma unroll
         for (int i = 0; i < 32; ++i) cv[i] = 0.f;
         const int nvec = jb.extra == 1 ? 1 : (jb.extra == 2 ? 3 : 0);
+        const bool do_bias = (jb.db_off >= 0 || jb.extra == 3) && ck < jb.z_blocks * 8;
+        const bool do_ex = nvec > 0 && ck < jb.a_blocks * 8;
         for (int tile = t_begin; tile < t_end; ++tile) {
           const int ray = p.ray_index ? p.ray_index[tile] : tile;
-          float tsum = 0.f;
+          float tsum[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) tsum[e] = 0.f;
           for (int half = 0; half < 2; ++half) {
             mbar_wait(bar_full(stage), phase);
-            const uint8_t* st = smem + stage * kWgStageBytes;
-            if (jb.db_off >= 0 || jb.extra == 3) {
-              if (t < jb.z_blocks * 64) {
-                const uint8_t* zb = st + (4 + (t >> 6)) * kHalfBlock + (t & 7) * 2;
-                const int c8 = (t & 63) >> 3;
-                float s = 0.f;
-#pragma unroll 8
-                for (int r = 0; r < 64; ++r)
-                  s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(zb + (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4)));
-                tsum += s;
+            const uint32_t st = sbase + stage * kWgStageBytes;
+            if (do_bias) {
+              const uint32_t zb = st + (4 + (ck >> 3)) * kHalfBlock;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = rg + 8 * i;          // r & 7 == rg
+                const float4 w = lds128_volatile(zb + (r >> 3) * 1024 + rg * 128 + (((ck & 7) ^ rg) << 4));
+                const uint32_t u[4] = {__float_as_uint(w.x), __float_as_uint(w.y), __float_as_uint(w.z), __float_as_uint(w.w)};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { tsum[2 * e] += __uint_as_float(u[e] << 16); tsum[2 * e + 1] += __uint_as_float(u[e] & 0xFFFF0000u); }
               }
             }
-            if (nvec > 0 && t < jb.a_blocks * 64) {
-              const uint8_t* ab = st + (t >> 6) * kHalfBlock + (t & 7) * 2;
-              const int c8 = (t & 63) >> 3;
+            if (do_ex) {
+              const uint32_t ab = st + (ck >> 3) * kHalfBlock;
               const float* vec = (jb.extra == 1 ? p.d_raw_density + (size_t)ray * kTileM : p.d_raw_rgb + (size_t)ray * kTileM * 3) +
                                  (size_t)half * 64 * nvec;
-              for (int r = 0; r < 64; ++r) {
-                const float a = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(ab + (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4)));
-                for (int jv = 0; jv < nvec; ++jv) {
-                  const float g = __ldg(vec + r * nvec + jv);
-                  ex[jv] = fmaf(a, g, ex[jv]);
-                  if (t == 0) exb[jv] += g;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = rg + 8 * i;
+                const float4 w = lds128_volatile(ab + (r >> 3) * 1024 + rg * 128 + (((ck & 7) ^ rg) << 4));
+                const uint32_t u[4] = {__float_as_uint(w.x), __float_as_uint(w.y), __float_as_uint(w.z), __float_as_uint(w.w)};
+                float g[3];
+                for (int jv = 0; jv < 3; ++jv) g[jv] = jv < nvec ? __ldg(vec + r * nvec + jv) : 0.f;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a0 = __uint_as_float(u[e] << 16), a1 = __uint_as_float(u[e] & 0xFFFF0000u);
+#pragma unroll
+                  for (int jv = 0; jv < 3; ++jv) { ex[2 * e][jv] = fmaf(a0, g[jv], ex[2 * e][jv]); ex[2 * e + 1][jv] = fmaf(a1, g[jv], ex[2 * e + 1][jv]); }
                 }
+                if (ck == 0)
+                  for (int jv = 0; jv < 3; ++jv) exb[jv] += g[jv];
               }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty(stage));
             if (++stage == kWgStages) { stage = 0; phase ^= 1; }
           }
-          bsum += tsum;
-          if (jb.extra == 3 && t < 128) {
-            const float* ve = p.cond + (size_t)ray * p.cond_dim;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < p.cond_dim) cv[i] = fmaf(__ldg(ve + i), tsum, cv[i]);
+          for (int e = 0; e < 8; ++e) bsum[e] += tsum[e];
+          if (jb.extra == 3) {
+            // view part: d kernel[width + i][c] += enc_i(ray) * (column sum of dZ_cond over this tile's 128 samples)
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (ck < 16) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) s_cs[rg * 128 + ck * 8 + e] = tsum[e];
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (t < 128) {
+              float tot = 0.f;
+#pragma unroll
+              for (int g8 = 0; g8 < 8; ++g8) tot += s_cs[g8 * 128 + t];
+              const float* ve = p.cond + (size_t)ray * p.cond_dim;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < p.cond_dim) cv[i] = fmaf(__ldg(ve + i), tot, cv[i]);
+            }
           }
         }
-        // per-CTA partial sums -> global gradient
-        if (jb.db_off >= 0 && t < jb.n_valid) red_add(p.d_params + jb.db_off + t, bsum);
-        if (nvec > 0 && t < jb.a_blocks * 64) {
-          for (int jv = 0; jv < nvec; ++jv) red_add(p.d_params + jb.ex_off + t * nvec + jv, ex[jv]);
-          if (t == 0 && jb.ex_b_off >= 0)
+        // per-thread partial sums -> global gradient (8 row groups x 148 CTAs add into every address)
+        if (jb.db_off >= 0 && do_bias) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (ck * 8 + e < jb.n_valid) red_add(p.d_params + jb.db_off + ck * 8 + e, bsum[e]);
+        }
+        if (do_ex) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            for (int jv = 0; jv < nvec; ++jv) red_add(p.d_params + jb.ex_off + (ck * 8 + e) * nvec + jv, ex[e][jv]);
+          if (ck == 0 && jb.ex_b_off >= 0)
             for (int jv = 0; jv < nvec; ++jv) red_add(p.d_params + jb.ex_b_off + jv, exb[jv]);
         }
         if (jb.extra == 3 && t < 128) {
@@ -250,7 +284,7 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
   }
 }
 
-constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 256 + 1024;
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 128 + 8 * 128 * 4 + 1024;
 
 // Builds the job list for a topology.  Tile records: saved activations = [layer g][W/64 blocks] for the depth+1 trunk /
 // bottleneck layers, then 2 blocks of the condition layer's activation; dz has the same record shape (dz of layer g at
