@@ -155,7 +155,7 @@ def run_reference(args, rank, world):
                             rays_per_step=n, note="CPU restatement (oracle/durf_oracle.py) of the JAX reference; JAX is not installable here"),
                 cpu_baseline=dict(value=v, unit="rays/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=v, unit="rays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(mlp, c2w, centers, ext_np):
@@ -273,7 +273,24 @@ def train_bench(dev, rank, world, steps, warmup, precision):
                 gpu_launches=int(launches), loss=loss, bg_mlp_tflops_algorithmic=flops / (ms * 1e-3) / 1e12)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL banners, library chatter) was
+    re-routed to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                       # NCCL prints its version banner on stdout: keep stdout for the JSON line only
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -315,7 +332,7 @@ def main():
     if args.train_only:
         t = train_bench(dev, rank, world, args.train_steps, 3, args.precision)
         if rank == 0:
-            print(json.dumps(t), flush=True)
+            emit(t)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -433,7 +450,7 @@ def main():
         line["train"] = train
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(mlp, c2w, centers, ext_np)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
