@@ -137,6 +137,47 @@ __device__ __forceinline__ float feature_value(const float* __restrict__ g6, int
   return e;
 }
 
+// Tensor-core path (features leave as bf16, half-ulp 2^-9): all 2*3*10 encodings of a sample from THREE accurate sincosf
+// calls, the higher octaves by angle doubling (sin 2y = 2 s c, cos 2y = 1 - 2 s^2; the error doubles per octave and stays
+// below 1e-4 at 2^9, 20x under the bf16 rounding of the stored value) and one ex2 per (octave, axis).  The fp32 output
+// path below keeps the reference's exact sequence (sin(y + fl32(pi/2)) with the 100*pi wrap, math.py:35-36) instead.
+// Writes the sample's 128-byte row of the SWIZZLE_128B tile image.
+template <bool weighted>
+__device__ __forceinline__ void encode_row_bf16(const Gauss& g, int min_deg, const float* __restrict__ s_w,
+                                                uint8_t* __restrict__ tile_base, int row) {
+  constexpr int D = 10;
+  float feat[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) feat[i] = 0.f;
+  constexpr int o = weighted ? 3 : 0;
+  const float sc0 = pow2i(min_deg);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (weighted) feat[d] = g.mean[d];
+    float sn, cs;
+    sincosf(g.mean[d] * sc0, &sn, &cs);
+    float yv = g.var[d] * (sc0 * sc0) * (-0.5f * 1.44269504088896341f);
+#pragma unroll
+    for (int l = 0; l < D; ++l) {
+      const float e = exp2f(yv);
+      feat[o + 3 * l + d] = e * sn;
+      feat[o + 3 * D + 3 * l + d] = e * cs;
+      const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * (sn * sn);
+      sn = s2; cs = c2;
+      yv = yv * 4.f;
+    }
+  }
+  if (weighted) {
+#pragma unroll
+    for (int i = 0; i < 6 * D; ++i) feat[3 + i] = s_w[i / 6] * feat[3 + i];     // mip.py:220: weight index i // 6
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<uint4*>(tile_base + sw128_offset(row, c)) =
+        make_uint4(pack_bf16x2(feat[8 * c], feat[8 * c + 1]), pack_bf16x2(feat[8 * c + 2], feat[8 * c + 3]),
+                   pack_bf16x2(feat[8 * c + 4], feat[8 * c + 5]), pack_bf16x2(feat[8 * c + 6], feat[8 * c + 7]));
+}
+
 __global__ void __launch_bounds__(128)
 raymarch_fwd_kernel(const RayMarchParams p) {
   extern __shared__ float smem[];
@@ -163,8 +204,15 @@ raymarch_fwd_kernel(const RayMarchParams p) {
     const float radius = a.radii[ray];
     const bool has_mult = a.ray_mult != nullptr;
     const float mult = has_mult ? a.ray_mult[ray] : 1.f;
+    const bool fast_tiles = (a.flags & DURF_RM_OUT_BF16_TILE) && p.D == 10;
     for (int n = lane; n < N; n += 32) {
       const Gauss g = sample_gaussian(a, o, d, radius, mult, has_mult, s_t[n], s_t[n + 1]);
+      if (fast_tiles) {
+        uint8_t* tile_base = reinterpret_cast<uint8_t*>(a.features) + ((size_t)m * N / 128) * (128 * 128);
+        const int row = (int)(((size_t)m * N) % 128) + n;
+        if (weighted) encode_row_bf16<true>(g, a.min_deg, s_w, tile_base, row);
+        else encode_row_bf16<false>(g, a.min_deg, s_w, tile_base, row);
+      }
 #pragma unroll
       for (int i = 0; i < 3; ++i) { s_g[6 * n + i] = g.mean[i]; s_g[6 * n + 3 + i] = g.var[i]; }
       if (a.means) {
@@ -176,7 +224,9 @@ raymarch_fwd_kernel(const RayMarchParams p) {
       }
     }
     __syncwarp();
-    if (a.flags & DURF_RM_OUT_BF16_TILE) {
+    if (fast_tiles) {
+      // rows already written by encode_row_bf16
+    } else if (a.flags & DURF_RM_OUT_BF16_TILE) {
       // 16-byte chunks: item i -> (sample i/8, chunk i%8); a warp store covers 4 samples = 512 contiguous bytes.
       uint8_t* tile_base = reinterpret_cast<uint8_t*>(a.features) + ((size_t)m * N / 128) * (128 * 128);
       const int row0 = (int)(((size_t)m * N) % 128);
