@@ -72,6 +72,31 @@ struct TcParams {
   ChunkSched chunks[kMaxChunks];
 };
 
+// Epilogue arithmetic of one 32-column group, specialised per layer kind so that the unrolled body has no branches:
+// KIND 0: relu(acc + bias) -> bf16; KIND 1: the same + fp32 partial dot product with the density head; KIND 2: linear.
+template <int KIND>
+__device__ __forceinline__ void epi_pack(const uint32_t (&v)[32], const float4 (&b4)[8], uint32_t wden_addr, float& den,
+                                         uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 a = add2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), make_float2(b4[j].x, b4[j].y));
+    const float2 b = add2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]), make_float2(b4[j].z, b4[j].w));
+    if (KIND == 0) {
+      pk[2 * j] = cvt_bf16x2_relu(a.x, a.y);
+      pk[2 * j + 1] = cvt_bf16x2_relu(b.x, b.y);
+    } else if (KIND == 1) {
+      const float4 w4 = lds128(wden_addr + 16 * j);
+      const float r0 = fmaxf(a.x, 0.f), r1 = fmaxf(a.y, 0.f), r2 = fmaxf(b.x, 0.f), r3 = fmaxf(b.y, 0.f);
+      den = fmaf(r0, w4.x, den); den = fmaf(r1, w4.y, den); den = fmaf(r2, w4.z, den); den = fmaf(r3, w4.w, den);
+      pk[2 * j] = cvt_bf16x2(r0, r1);
+      pk[2 * j + 1] = cvt_bf16x2(r2, r3);
+    } else {
+      pk[2 * j] = cvt_bf16x2(a.x, a.y);
+      pk[2 * j + 1] = cvt_bf16x2(b.x, b.y);
+    }
+  }
+}
+
 template <int W>
 struct TcCfg {
   static constexpr int NHALF = W / 128;                   // N-halves per trunk layer (every tcgen05.mma is M=128, N=128)
@@ -167,20 +192,21 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the schedule (uniform control flow), one elected lane issues =====
+    {
       constexpr uint32_t idesc = umma_idesc(128, 128);
       constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);     // SBO | version | SWIZZLE_128B
       uint32_t stage = 0, phase = 0;
       uint32_t ar_par[2] = {0, 0}, inp_par = 0;
       int it = 0;
       const bool tr = p.trace && blockIdx.x == 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       long long t_full = 0, t_ready = 0, t_inp = 0, t_begin = clock64(), tq = 0;
       const uint32_t inp_lo = ((sbase + C::OFF_INP) & 0x3FFFF) >> 4 | (1u << 16);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         for (int c = 0; c < p.n_chunks; ++c) {
           const ChunkSched ck = p.chunks[c];
-          const uint32_t d_addr = tmem_base + C::ACC_COL + ck.nh * 128;
+          const uint32_t d_addr = tmem_u + C::ACC_COL + ck.nh * 128;
           if (c == 0) {
             if (tr) tq = clock64();
             mbar_wait(bar_inp_full, inp_par); inp_par ^= 1;
@@ -195,7 +221,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
           tc_fence_after();
           const uint32_t b_lo = (((sbase + C::OFF_RING + stage * C::STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
           if (!ck.inp) {
-            const uint32_t a_buf = tmem_base + C::ACT_COL + (ck.g & 1) * (W / 2);     // written by the epilogue of layer g-1
+            const uint32_t a_buf = tmem_u + C::ACT_COL + (ck.g & 1) * (W / 2);     // written by the epilogue of layer g-1
 #pragma unroll
             for (int kb = 0; kb < C::KB; ++kb) {
               if (kb < ck.nkb) {
@@ -207,23 +233,22 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
                 }
 #pragma unroll
                 for (int k16 = 0; k16 < 4; ++k16)
-                  umma_ts(d_addr, a_buf + kb * 32 + k16 * 8, b_lo + ((kb * kBlockBytes + k16 * 32) >> 4), desc_hi, idesc,
+                  umma_ts_conv(d_addr, a_buf + kb * 32 + k16 * 8, b_lo + ((kb * kBlockBytes + k16 * 32) >> 4), desc_hi, idesc,
                           (ck.first && kb == 0 && k16 == 0) ? 0u : 1u);
               }
             }
           } else {
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16)
-              umma_ss(d_addr, inp_lo + ((k16 * 32) >> 4), b_lo + ((k16 * 32) >> 4), desc_hi, idesc, (ck.first && k16 == 0) ? 0u : 1u);
+              umma_ss_conv(d_addr, inp_lo + ((k16 * 32) >> 4), b_lo + ((k16 * 32) >> 4), desc_hi, idesc, (ck.first && k16 == 0) ? 0u : 1u);
           }
-          if (ck.last) tc_commit(bar_acc_full(ck.nh));      // the epilogue releases the ring stage(s) and the input tile
+          if (ck.last) tc_commit_conv(bar_acc_full(ck.nh));      // the epilogue releases the ring stage(s) and the input tile
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if (tr) printf("durf mlp_tc trace: MMA thread: %d tiles, total %lld cyc; waiting weights %lld, epilogue(a_ready) %lld, features %lld\n",
+      if (tr && lane == 0) printf("durf mlp_tc trace: MMA thread: %d tiles, total %lld cyc; waiting weights %lld, epilogue(a_ready) %lld, features %lld\n",
                      it, clock64() - t_begin, t_full, t_ready, t_inp);
     }
-    __syncwarp();
   } else if (warp == 2) {
     // ===== feature-tile loader: the next tile's features arrive while the layers after the skip layer run =====
     if (lane == 0) {
@@ -262,7 +287,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     uint32_t af_par[2] = {0, 0};
     constexpr int NG = C::CPW / 32;               // 32-column groups per warp per half
     const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 128;
-    long long e_acc = 0, e_ld = 0, e_math = 0, e_st = 0, e_begin = clock64(), eq = 0;
+    long long e_acc = 0, e_ld = 0, e_math = 0, e_st = 0, e_begin = clock64(), eq = 0, e_m0 = 0, e_ld1 = 0, e_m1 = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int ray = p.ray_index ? p.ray_index[tile] : tile;
       // per-ray bias of the condition layer (b + W_view^T enc(viewdir), obbpose_model.py:343-350), precomputed per tile
@@ -292,30 +317,21 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
               float4 b4[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) b4[j] = lds128(sb + (i * 32 + 4 * j) * 4);
+              long long tq1 = 0;
+              if (tr && i == 1) tq1 = clock64();
               tmem_ld_wait();
               tmem_ld_pin(v[i]);
+              if (tr && i == 1) e_ld1 += clock64() - tq1;
               if (i + 1 < NG) tmem_ld32_issue(t_lane + C::ACC_COL + col0 + (i + 1) * 32, v[i + 1]);
               if (tr && i == 0) { e_ld += clock64() - eq; eq = clock64(); }
+              if (tr) tq1 = clock64();
               uint32_t pk[16];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 a = add2(__uint_as_float(v[i][4 * j]), __uint_as_float(v[i][4 * j + 1]), make_float2(b4[j].x, b4[j].y));
-                const float2 b = add2(__uint_as_float(v[i][4 * j + 2]), __uint_as_float(v[i][4 * j + 3]), make_float2(b4[j].z, b4[j].w));
-                if (L.kind == 0) {
-                  pk[2 * j] = cvt_bf16x2_relu(a.x, a.y);
-                  pk[2 * j + 1] = cvt_bf16x2_relu(b.x, b.y);
-                } else if (L.kind == 1) {
-                  const float4 w4 = lds128(sbase + C::OFF_WDEN + (col0 + i * 32 + 4 * j) * 4);
-                  const float r0 = fmaxf(a.x, 0.f), r1 = fmaxf(a.y, 0.f), r2 = fmaxf(b.x, 0.f), r3 = fmaxf(b.y, 0.f);
-                  den = fmaf(r0, w4.x, den); den = fmaf(r1, w4.y, den); den = fmaf(r2, w4.z, den); den = fmaf(r3, w4.w, den);
-                  pk[2 * j] = cvt_bf16x2(r0, r1);
-                  pk[2 * j + 1] = cvt_bf16x2(r2, r3);
-                } else {
-                  pk[2 * j] = cvt_bf16x2(a.x, a.y);
-                  pk[2 * j + 1] = cvt_bf16x2(b.x, b.y);
-                }
-              }
+              const uint32_t wden_addr = sbase + C::OFF_WDEN + (col0 + i * 32) * 4;
+              if (L.kind == 0) epi_pack<0>(v[i], b4, wden_addr, den, pk);
+              else if (L.kind == 1) epi_pack<1>(v[i], b4, wden_addr, den, pk);
+              else epi_pack<2>(v[i], b4, wden_addr, den, pk);
               tmem_st16(o_buf + (col0 + i * 32) / 2, pk);
+              if (tr) { if (i == 0) e_m0 += clock64() - tq1; else e_m1 += clock64() - tq1; }
               if (p.saved) {      // training: keep the activation (the A operand of wgrad, the ReLU mask of dgrad)
                 const int cc = col0 + i * 32;
                 uint8_t* blk = p.saved + ((size_t)tile * p.saved_blocks_per_tile + g * C::KB + (cc >> 6)) * kBlockBytes;
@@ -363,8 +379,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
         }
       }
       if (tr && tile + (int)gridDim.x >= num_tiles)
-        printf("durf mlp_tc trace: epilogue thread: total %lld cyc; waiting acc_full %lld, tmem ld %lld, math+st issue %lld, st wait %lld\n",
-               clock64() - e_begin, e_acc, e_ld, e_math, e_st);
+        printf("durf mlp_tc trace: epilogue thread: total %lld cyc; waiting acc_full %lld, tmem ld %lld, math+st issue %lld (g0 %lld, ld1 wait %lld, g1 %lld), st wait %lld\n",
+               clock64() - e_begin, e_acc, e_ld, e_math, e_m0, e_ld1, e_m1, e_st);
       // combine the two column slices of every row and write the raw outputs
       if (ch == 1) {
         s_part[row] = den; s_part[128 + row] = rgb[0]; s_part[256 + row] = rgb[1]; s_part[384 + row] = rgb[2];
