@@ -11,7 +11,7 @@
 //     the next layer starts on the K blocks produced by half 0 while the epilogue of half 1 is still running, so the
 //     tensor pipe only waits for an epilogue if that epilogue is slower than half a layer of MMAs.
 // Warp roles (384 threads): warp 0 = weight producer (cp.async.bulk of pre-tiled, pre-swizzled bf16 chunks into an
-// mbarrier ring), warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator + feature-tile loader, warp 3 = stage releaser,
+// mbarrier ring), warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator + feature-tile loader, warp 3 idle,
 // warps 4-11 = epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter split the columns of a half).
 // The skip connection (obbpose_model.py:332-333) is an extra K block read from the still-resident input tile (smem,
 // ".ss" form); the view direction (constant along a ray) enters the condition layer as a per-tile fp32 bias
@@ -261,23 +261,6 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       }
     }
     __syncwarp();
-  } else if (warp == 3) {
-    // ===== stage releaser: when the MMAs of (layer, half) have retired, their weight stage(s) and, after the skip
-    // layer, the input tile are free.  (A tcgen05.commit per stage on the issuing thread would cost it ~190 cycles.)
-    if (lane == 0) {
-      uint32_t af_par[2] = {0, 0}, rel_stage = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
-        for (int g = 0; g < p.G; ++g) {
-          const LayerSched& L = p.sched[g];
-          for (int h = 0; h < L.n_halves; ++h) {
-            mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
-            const int n_rel = (L.n_act_kb > 0 ? 1 : 0) + L.uses_inp;
-            for (int r = 0; r < n_rel; ++r) { mbar_arrive(bar_empty(rel_stage)); if (++rel_stage == C::STAGES) rel_stage = 0; }
-            if (L.last_inp_use && h == L.n_halves - 1) mbar_arrive(bar_inp_empty);
-          }
-        }
-    }
-    __syncwarp();
   } else if (warp >= 4) {
     // ===== epilogue: thread = accumulator row = sample; warps q and q+4 share TMEM lane quarter q =====
     const int q = warp & 3;
@@ -286,6 +269,11 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t af_par[2] = {0, 0};
     constexpr int NG = C::CPW / 32;               // 32-column groups per warp per half
+    // The first epilogue thread also frees weight stages / the input tile once their MMAs have retired.  It must be a
+    // thread whose progress the MMA issuer depends on: a passive observer of acc_full could fall two completions behind
+    // (the ring lets the issuer run three chunks ahead) and miss a phase.
+    const bool releaser = threadIdx.x == 128;
+    uint32_t rel_stage = 0;
     const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 128;
     long long e_acc = 0, e_ld = 0, e_math = 0, e_st = 0, e_begin = clock64(), eq = 0, e_m0 = 0, e_ld1 = 0, e_m1 = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -305,6 +293,11 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
           if (tr) eq = clock64();
           mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
           if (tr) { e_acc += clock64() - eq; eq = clock64(); }
+          if (releaser) {
+            const int n_rel = (L.n_act_kb > 0 ? 1 : 0) + L.uses_inp;
+            for (int r = 0; r < n_rel; ++r) { mbar_arrive(bar_empty(rel_stage)); if (++rel_stage == C::STAGES) rel_stage = 0; }
+            if (L.last_inp_use && h == L.n_halves - 1) mbar_arrive(bar_inp_empty);
+          }
           tc_fence_after();
           uint32_t v[NG][32];
           tmem_ld32_issue(t_lane + C::ACC_COL + col0, v[0]);

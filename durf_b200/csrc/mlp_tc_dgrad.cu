@@ -60,10 +60,38 @@ struct DgCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
+// Masking / packing of one 32-column group, specialised per stage kind (0: linear, 1: + density term and mask, 2: mask)
+// so the unrolled body is branch-free.  Writes the group's 64 bytes of the dZ tile image row and returns the packed words.
+template <int KIND>
+__device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], const uint4 (&m4)[4], float gden, uint32_t wden_addr,
+                                        uint8_t* __restrict__ out_row_base, int row, int chunk0, uint32_t (&pk)[16]);
+
 // keep a packed bf16 pair where the matching activation halfwords are non-zero (ReLU outputs are +0 or positive)
 __device__ __forceinline__ uint32_t mask_pair(uint32_t packed, uint32_t act) {
   const uint32_t m = ((act & 0xFFFFu) ? 0xFFFFu : 0u) | ((act & 0xFFFF0000u) ? 0xFFFF0000u : 0u);
   return packed & m;
+}
+
+template <int KIND>
+__device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], const uint4 (&m4)[4], float gden, uint32_t wden_addr,
+                                        uint8_t* __restrict__ out_blk, int row, int chunk0, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int c8 = 0; c8 < 4; ++c8) {
+    const uint32_t aw[4] = {m4[c8].x, m4[c8].y, m4[c8].z, m4[c8].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v0 = __uint_as_float(v[c8 * 8 + 2 * e]), v1 = __uint_as_float(v[c8 * 8 + 2 * e + 1]);
+      if (KIND == 1) {
+        const float2 wd = lds64(wden_addr + (c8 * 8 + 2 * e) * 4);
+        v0 = fmaf(gden, wd.x, v0); v1 = fmaf(gden, wd.y, v1);
+      }
+      uint32_t pr = cvt_bf16x2(v0, v1);
+      if (KIND != 0) pr = mask_pair(pr, aw[e]);
+      pk[c8 * 4 + e] = pr;
+    }
+    *reinterpret_cast<uint4*>(out_blk + sw128_offset(row, chunk0 + c8)) =
+        make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+  }
 }
 
 template <int W>
@@ -123,18 +151,19 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the schedule (uniform control flow), one elected lane issues =====
+    {
       constexpr uint32_t idesc = umma_idesc(128, 128);
       constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       uint32_t stage = 0, phase = 0, ar_par[2] = {0, 0}, pr_par = 0;
       int it = 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it)
         for (int s = 0; s < p.n_stages; ++s) {
           const DgStage S = p.st[s];
-          const uint32_t a_buf = tmem_base + C::ACT_COL + (s & 1) * (W / 2);
+          const uint32_t a_buf = tmem_u + C::ACT_COL + (s & 1) * (W / 2);
           for (int nh = 0; nh < S.n_halves; ++nh) {
-            const uint32_t d_addr = tmem_base + C::ACC_COL + nh * 128;
+            const uint32_t d_addr = tmem_u + C::ACC_COL + nh * 128;
             if (s == 0 && nh == 0) {
               if (it > 0)      // accumulators of the previous tile's last stage must have been drained
                 for (int h = 0; h < last_halves; ++h) { mbar_wait(bar_a_ready(h), ar_par[h]); ar_par[h] ^= 1; }
@@ -153,35 +182,23 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
                 }
 #pragma unroll
                 for (int k16 = 0; k16 < 4; ++k16)
-                  umma_ts(d_addr, a_buf + kb * 32 + k16 * 8, b_lo + ((kb * kBlockBytes + k16 * 32) >> 4), desc_hi, idesc,
+                  umma_ts_conv(d_addr, a_buf + kb * 32 + k16 * 8, b_lo + ((kb * kBlockBytes + k16 * 32) >> 4), desc_hi, idesc,
                           (kb == 0 && k16 == 0) ? 0u : 1u);
               }
             }
-            tc_commit(bar_acc_full(nh));
+            tc_commit_conv(bar_acc_full(nh));
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
     }
-    __syncwarp();
-  } else if (warp == 3) {
-    // ===== stage releaser =====
-    if (lane == 0) {
-      uint32_t af_par[2] = {0, 0}, rel_stage = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
-        for (int s = 0; s < p.n_stages; ++s)
-          for (int h = 0; h < p.st[s].n_halves; ++h) {
-            mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
-            mbar_arrive(bar_empty(rel_stage));
-            if (++rel_stage == C::STAGES) rel_stage = 0;
-          }
-    }
-    __syncwarp();
   } else if (warp >= 4) {
     // ===== epilogue: thread = sample row; warps q and q+4 share TMEM lane quarter q and split a half's 128 columns =====
     const int q = warp & 3, ch = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t af_par[2] = {0, 0};
+    const bool releaser = threadIdx.x == 128;     // an active participant frees the ring stages (see mlp_tc.cu)
+    uint32_t rel_stage = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int ray = p.ray_index ? p.ray_index[tile] : tile;
       const uint8_t* sv = p.saved + (size_t)tile * p.saved_blocks * kBlockBytes;
@@ -231,6 +248,7 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
             for (int c8 = 0; c8 < 4; ++c8) m4[c8] = *reinterpret_cast<const uint4*>(act + sw128_offset(row, c8));
           }
           mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
+          if (releaser) { mbar_arrive(bar_empty(rel_stage)); if (++rel_stage == C::STAGES) rel_stage = 0; }
           tc_fence_after();
           uint8_t* out = dzt + (size_t)(S.out_slot + (col0 >> 6)) * kBlockBytes;
 #pragma unroll
@@ -240,23 +258,10 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
             tmem_ld_wait();
             tmem_ld_pin(v);
             uint32_t pk[16];
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              const uint32_t aw[4] = {m4[c8].x, m4[c8].y, m4[c8].z, m4[c8].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float v0 = __uint_as_float(v[c8 * 8 + 2 * e]), v1 = __uint_as_float(v[c8 * 8 + 2 * e + 1]);
-                if (S.kind == 1) {
-                  const float2 wd = lds64(sbase + C::OFF_WDEN + (col0 + i * 32 + c8 * 8 + 2 * e) * 4);
-                  v0 = fmaf(gden, wd.x, v0); v1 = fmaf(gden, wd.y, v1);
-                }
-                uint32_t pr = cvt_bf16x2(v0, v1);
-                if (S.kind != 0) pr = mask_pair(pr, aw[e]);
-                pk[c8 * 4 + e] = pr;
-              }
-              *reinterpret_cast<uint4*>(out + sw128_offset(row, i * 4 + c8)) =
-                  make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
-            }
+            const uint32_t wden_addr = sbase + C::OFF_WDEN + (col0 + i * 32) * 4;
+            if (S.kind == 0) dg_pack<0>(v, m4, gden, wden_addr, out, row, i * 4, pk);
+            else if (S.kind == 1) dg_pack<1>(v, m4, gden, wden_addr, out, row, i * 4, pk);
+            else dg_pack<2>(v, m4, gden, wden_addr, out, row, i * 4, pk);
             if (i == 0 && S.kind != 0) {       // mask rows of the second 32-column group
 #pragma unroll
               for (int c8 = 0; c8 < 4; ++c8) m4[c8] = *reinterpret_cast<const uint4*>(act + sw128_offset(row, 4 + c8));

@@ -114,9 +114,10 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer: D[features of A, columns of dZ] += A^T dZ over the 64 samples of a stage (4 x K=16) =====
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0) {      // the whole warp walks the schedule (uniform control flow), one elected lane issues
       constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       uint32_t stage = 0, phase = 0, free_par = 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       for (int j = 0; j < p.n_jobs; ++j) {
         const WgradJob jb = p.jobs[j];
         if (jb.z_blocks > 0 && j > 0) { mbar_wait(bar_acc_free, free_par); free_par ^= 1; tc_fence_after(); }   // previous accumulator was read out
@@ -135,17 +136,16 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
                 const uint32_t a_lo = (((st + mt * 2 * kHalfBlock) & 0x3FFFF) >> 4) | (a_lbo << 16);
 #pragma unroll
                 for (int k16 = 0; k16 < 4; ++k16)
-                  umma_ss(tmem_base + mt * N, a_lo + ((k16 * 2048) >> 4), b_lo + ((k16 * 2048) >> 4), desc_hi, idesc,
+                  umma_ss_conv(tmem_u + mt * N, a_lo + ((k16 * 2048) >> 4), b_lo + ((k16 * 2048) >> 4), desc_hi, idesc,
                           (tile == t_begin && half == 0 && k16 == 0) ? 0u : 1u);
               }
             }
-            tc_commit(bar_empty(stage));
+            tc_commit_conv(bar_empty(stage));
             if (++stage == kWgStages) { stage = 0; phase ^= 1; }
           }
-        if (jb.z_blocks > 0) tc_commit(bar_acc_done);
+        if (jb.z_blocks > 0) tc_commit_conv(bar_acc_done);
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ===== auxiliary warps: bias / narrow-head gradients from the stages in shared memory, then the accumulator read-out.
     // Thread (rg, ck) of the 256 owns the 16-byte piece ck (8 consecutive columns) of the rows rg, rg+8, ... of a stage, so
