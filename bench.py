@@ -431,8 +431,13 @@ def main():
     # roofline of the dominant kernel: every launch covers <= chunk rays x 128 samples, two levels per frame
     flops = float(n_rays) * N_SAMPLES * 2 * MLP_FLOP_PER_SAMPLE * steps
     ach = flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+    traffic = None                                        # DRAM bytes per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r01_mlp_fwd_traffic.json")
+    if os.path.exists(tpath) and n_mlp > 0:
+        traffic = json.load(open(tpath))["dram_bytes_per_tile"] * (float(n_rays) * 2 * steps / n_mlp)
     roof = dict(bound="tensor", kernel="mlp_tc_fwd_kernel<256>", achieved=ach, peak=peaks["tf_sustained"], unit="TFLOP/s",
-                frac=ach / peaks["tf_sustained"], traffic=None, peak_source=peaks["src"] + " (sustained bf16 cuBLAS)",
+                frac=ach / peaks["tf_sustained"], traffic=traffic, traffic_unit="bytes per launch (ncu dram read+write, profiles/r01_mlp_fwd_traffic.json)",
+                flops_per_launch=flops / max(n_mlp, 1), peak_source=peaks["src"] + " (sustained bf16 cuBLAS)",
                 launches=n_mlp, avg_launch_ms=mlp_ms / max(n_mlp, 1), share_of_step=mlp_ms / (ms_resident * steps))
     line = dict(metric="rays/sec (render, 2x128 samples)", value=value, unit="rays/s", n_gpus=world, steps=steps, warmup=warmup,
                 ms_per_step=ms_resident, higher_is_better=True, scaling="weak", vs_baseline=None,
