@@ -103,6 +103,19 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c
   return (r >> 3) * 1024u + (r & 7u) * 128u + ((c ^ (r & 7u)) << 4);
 }
 
+// 32-byte store of the logical 16-byte chunks (c, c+1), c even, of row r of a SWIZZLE_128B block image: they occupy one
+// aligned physical pair (swapped on odd rows), so a single STG.256 fills a whole 32-byte sector.
+__device__ __forceinline__ void st_sw128_pair(uint8_t* blk, uint32_t r, uint32_t c, const uint32_t (&w)[8]) {
+  const uint32_t r7 = r & 7u;
+  uint8_t* dst = blk + (r >> 3) * 1024u + r7 * 128u + (((c ^ r7) & ~1u) << 4);
+  if (r7 & 1u)
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[0]),
+                 "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+  else
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+                 "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

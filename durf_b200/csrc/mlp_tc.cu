@@ -329,9 +329,11 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
                 const int cc = col0 + i * 32;
                 uint8_t* blk = p.saved + ((size_t)tile * p.saved_blocks_per_tile + g * C::KB + (cc >> 6)) * kBlockBytes;
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4)
-                  *reinterpret_cast<uint4*>(blk + sw128_offset(row, ((cc & 63) >> 3) + q4)) =
-                      make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+                for (int q2 = 0; q2 < 2; ++q2) {
+                  const uint32_t w8[8] = {pk[8 * q2], pk[8 * q2 + 1], pk[8 * q2 + 2], pk[8 * q2 + 3], pk[8 * q2 + 4], pk[8 * q2 + 5],
+                                          pk[8 * q2 + 6], pk[8 * q2 + 7]};
+                  st_sw128_pair(blk, (uint32_t)row, ((cc & 63) >> 3) + 2 * q2, w8);
+                }
               }
             }
             if (tr) { e_math += clock64() - eq; eq = clock64(); }

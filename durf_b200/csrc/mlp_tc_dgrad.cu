@@ -89,8 +89,12 @@ __device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], const uint4 (&m
       if (KIND != 0) pr = mask_pair(pr, aw[e]);
       pk[c8 * 4 + e] = pr;
     }
-    *reinterpret_cast<uint4*>(out_blk + sw128_offset(row, chunk0 + c8)) =
-        make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+  }
+#pragma unroll
+  for (int q2 = 0; q2 < 2; ++q2) {
+    const uint32_t w8[8] = {pk[8 * q2], pk[8 * q2 + 1], pk[8 * q2 + 2], pk[8 * q2 + 3], pk[8 * q2 + 4], pk[8 * q2 + 5], pk[8 * q2 + 6],
+                            pk[8 * q2 + 7]};
+    st_sw128_pair(out_blk, (uint32_t)row, chunk0 + 2 * q2, w8);
   }
 }
 

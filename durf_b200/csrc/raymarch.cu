@@ -151,34 +151,41 @@ __device__ __forceinline__ void encode_row_bf16(const Gauss& g, int min_deg, con
   for (int i = 0; i < 64; ++i) feat[i] = 0.f;
   constexpr int o = weighted ? 3 : 0;
   const float sc0 = pow2i(min_deg);
+  float sn[3], cs[3], yv[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     if (weighted) feat[d] = g.mean[d];
-    float sn, cs;
-    sincosf(g.mean[d] * sc0, &sn, &cs);
-    float yv = g.var[d] * (sc0 * sc0) * (-0.5f * 1.44269504088896341f);
+    sincosf(g.mean[d] * sc0, &sn[d], &cs[d]);
+    yv[d] = g.var[d] * (sc0 * sc0) * (-0.5f * 1.44269504088896341f);
+  }
+  // octave-major order: a pair of neighbouring features is complete within two octaves, so it can be packed early
 #pragma unroll
-    for (int l = 0; l < D; ++l) {
-      const float e = exp2f(yv);
-      feat[o + 3 * l + d] = e * sn;
-      feat[o + 3 * D + 3 * l + d] = e * cs;
-      const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * (sn * sn);
-      sn = s2; cs = c2;
-      yv = yv * 4.f;
+  for (int l = 0; l < D; ++l) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float e = exp2f(yv[d]);
+      feat[o + 3 * l + d] = e * sn[d];
+      feat[o + 3 * D + 3 * l + d] = e * cs[d];
+      const float s2 = 2.f * sn[d] * cs[d], c2 = 1.f - 2.f * (sn[d] * sn[d]);
+      sn[d] = s2; cs[d] = c2;
+      yv[d] = yv[d] * 4.f;
     }
   }
   if (weighted) {
 #pragma unroll
     for (int i = 0; i < 6 * D; ++i) feat[3 + i] = s_w[i / 6] * feat[3 + i];     // mip.py:220: weight index i // 6
   }
+  // 32-byte stores (STG.256): every store fills a whole sector of the swizzled image
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
-    *reinterpret_cast<uint4*>(tile_base + sw128_offset(row, c)) =
-        make_uint4(pack_bf16x2(feat[8 * c], feat[8 * c + 1]), pack_bf16x2(feat[8 * c + 2], feat[8 * c + 3]),
-                   pack_bf16x2(feat[8 * c + 4], feat[8 * c + 5]), pack_bf16x2(feat[8 * c + 6], feat[8 * c + 7]));
+  for (int k = 0; k < 4; ++k) {
+    uint32_t w[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[e] = pack_bf16x2(feat[16 * k + 2 * e], feat[16 * k + 2 * e + 1]);
+    st_sw128_pair(tile_base, (uint32_t)row, 2 * k, w);
+  }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 raymarch_fwd_kernel(const RayMarchParams p) {
   extern __shared__ float smem[];
   const DurfRaymarchArgs& a = p.a;
