@@ -94,9 +94,10 @@ class MipNerfModel:
         parameters live in `variables`, as `self.param('box_centers', ...)` does after initialisation).
         When `ctx` (a dict) is given the forward keeps what the backward pass needs in it."""
         prec = L.PREC_BF16 if self.precision == 'bf16' else L.PREC_FP32
-        if ctx is not None and prec != L.PREC_FP32 and self.dynamics and not (self.no_pose_opt and self.no_yaw_opt):
-            raise L.DurfError("the box-pose gradient (no_pose_opt/no_yaw_opt = False) needs precision='fp32': the tensor-core "
-                              "backward produces no input gradient")
+        # Joint box-pose optimisation needs the gradient w.r.t. the object MLPs' input features, which only the fp32 kernels
+        # produce: with precision='bf16' the object MLPs then run in fp32 (few rays hit a box), the background stays bf16.
+        pose_train = ctx is not None and self.dynamics and not (self.no_pose_opt and self.no_yaw_opt)
+        obj_prec = L.PREC_FP32 if pose_train else prec
         N = self.num_samples
         origins, dirs = ops.f32(rays.origins), ops.f32(rays.directions)
         B = origins.shape[0]
@@ -119,7 +120,7 @@ class MipNerfModel:
             for k in range(K):
                 idx, cnt = ops.compact_hits(hit, k)
                 m_host = None
-                if prec == L.PREC_FP32 or ctx is not None:
+                if obj_prec == L.PREC_FP32 or ctx is not None:
                     m_host = int(cnt.item())                                 # parity / training size their buffers exactly
                 obj_lists.append((idx, cnt, m_host))
         bt, ot = self.bg_topology(), self.box_topology()
@@ -130,7 +131,7 @@ class MipNerfModel:
         ret = []
         t_vals = weights = None
         if ctx is not None:
-            ctx.update(dict(fe=fe, viewenc=viewenc, obj_lists=obj_lists, levels=[], B=B, K=K, ts=ts_i, alpha=alpha,
+            ctx.update(dict(fe=fe, viewenc=viewenc, obj_lists=obj_lists, levels=[], B=B, K=K, ts=ts_i, alpha=alpha, obj_prec=obj_prec,
                             white_bkgd=white_bkgd, rand_bkgd=rand_bkgd, rays=rays, box=box, radii=radii))
         for i_level in range(self.num_levels):
             common = dict(min_deg=self.min_deg_point, max_deg=self.max_deg_point, ray_shape=self.ray_shape,
@@ -155,9 +156,10 @@ class MipNerfModel:
                         continue
                     rows = m_host if m_host is not None else B
                     rmo = ops.raymarch(origins_s, dirs_s, radii, N, t_vals=t_vals, weighted=True, alpha=alpha, ray_index=idx,
-                                       count=None if m_host is not None else cnt, rows=rows, **common)
+                                       count=None if m_host is not None else cnt, rows=rows,
+                                       **dict(common, bf16_tiles=obj_prec == L.PREC_BF16))
                     _, _, saved_o = ops.mlp_fwd(ot, rmo['features'], viewenc, variables.blob(f'BoxMLP_{k}'), M=rows, N=N,
-                                                precision=prec, packed=variables.packed.get(f'BoxMLP_{k}'), ray_index=idx,
+                                                precision=obj_prec, packed=variables.packed.get(f'BoxMLP_{k}'), ray_index=idx,
                                                 count=None if m_host is not None else cnt, accumulate=True, raw_rgb=raw_rgb,
                                                 raw_density=raw_density, save=ctx is not None)
                     if lvl_ctx is not None:
@@ -204,7 +206,7 @@ class MipNerfModel:
                 idx = ctx['obj_lists'][k][0]
                 dfeat = ops.mlp_bwd(ot, o['feat'], viewenc, variables.blob(f'BoxMLP_{k}'), o['saved'], g_rgb, g_den,
                                     variables.blob_of(d_flat, f'BoxMLP_{k}'), M=o['rows'], N=N, ray_index=idx,
-                                    want_d_features=pose_opt, precision=prec, packed=variables.packed.get(f'BoxMLP_{k}'),
+                                    want_d_features=pose_opt, precision=ctx['obj_prec'], packed=variables.packed.get(f'BoxMLP_{k}'),
                                     count=o.get('count'))
                 if pose_opt:
                     go = torch.zeros(B, 3, device=d_flat.device)

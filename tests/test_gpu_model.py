@@ -214,3 +214,31 @@ def test_train_step_tensor_core():
         cos = float(a @ b / (a.norm() * b.norm()))
         assert cos >= 0.97, f"{name}: gradient cosine {cos:.5f}"
         assert abs(float(a.norm() / b.norm()) - 1.0) <= 0.1, f"{name}: gradient norm ratio {float(a.norm() / b.norm()):.4f}"
+
+
+def test_pose_optimisation_with_tensor_core_background():
+    """C5 with precision='bf16': the background MLP trains on the tensor cores, the object MLPs fall to the fp32 kernels
+    (they own the input gradient that reaches the SE(3) box parameters).  d box_centers vs fp64 oracle: cosine >= 0.98."""
+    from durf_b200.train import TrainState, train_step
+    from durf_b200.utils import Config
+    sc = H.scene(B=256, K=2, seed=31)
+    cfg = O.ModelConfig(no_pose_opt=False, no_yaw_opt=False)
+    p64 = H.oracle_params(sc, torch.float64)
+    p64['box_centers'].requires_grad_(True)
+    ret = _oracle_forward(sc, 3, True, 4.5, cfg, dtype=torch.float64, params=p64)
+    tg = {k: torch.from_numpy(v) for k, v in sc['targets'].items()}
+    loss, _ = O.loss_fn(ret, H.oracle_rays(sc, torch.float64), tg['pixels'].double(), tg['depth'].double(), tg['sky'].double(), eps=3.0)
+    g64 = torch.autograd.grad(loss, p64['box_centers'])[0].reshape(-1)
+    model = _model(precision='bf16', no_pose_opt=False, no_yaw_opt=False)
+    v = H.cuda_variables(sc, model)
+    state = TrainState.create(v)
+    batch = dict(rays=H.cuda_rays(sc), ext=torch.from_numpy(sc['ext']).cuda(), ts=torch.tensor([3]),
+                 pixels=tg['pixels'].cuda(), depth=tg['depth'].cuda(), sky=tg['sky'].cuda())
+    rng = dict(t_rand=torch.from_numpy(sc['t_rand']).cuda(), u_rand=torch.from_numpy(sc['u_rand']).cuda())
+    state, st = train_step(model, Config(grad_max_val=0.0, grad_max_norm=0.0), rng, state, batch, lr=1e-3, eps=3.0, alpha=4.5)
+    assert abs(float(st['loss']) - float(loss)) <= 1e-2 * max(1.0, abs(float(loss)))
+    o, n = v.slots['box_centers']
+    got = st['grad'][o:o + n].double().cpu()
+    assert float(g64.norm()) > 0
+    cos = float(got @ g64 / (got.norm() * g64.norm()))
+    assert cos >= 0.98, f"d box_centers cosine {cos:.4f}"
