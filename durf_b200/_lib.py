@@ -37,6 +37,11 @@ class DurfError(RuntimeError):
     pass
 
 
+class Camera(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("focal", C.c_float), ("c2w", C.c_float * 12),
+                ("near", C.c_float), ("far", C.c_float)]
+
+
 class MlpTopology(C.Structure):
     _fields_ = [("in_dim", C.c_int32), ("width", C.c_int32), ("depth", C.c_int32), ("skip", C.c_int32),
                 ("cond_dim", C.c_int32), ("cond_width", C.c_int32)]
@@ -90,6 +95,7 @@ SIGNATURES = {
     "durf_reset_launch_count": (None, []),
     "durf_mlp_param_count": (_i64, [C.POINTER(MlpTopology)]),
     "durf_mlp_param_offset": (_i64, [C.POINTER(MlpTopology), _i32, C.POINTER(_i32), C.POINTER(_i32)]),
+    "durf_generate_rays": (C.c_int, [_vp, C.POINTER(Camera), _i32, _i32] + [_vp] * 7),
     "durf_aa2matrix_fwd": (C.c_int, [_vp, _i32, _vp, _vp]),
     "durf_obb_frontend_fwd": (C.c_int, [_vp, _i32, _i32] + [_vp] * 13),
     "durf_obb_frontend_bwd": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),

@@ -39,6 +39,25 @@ def reset_launch_count() -> None:
     L.load().durf_reset_launch_count()
 
 
+# ---- N2: ray generation on the device ------------------------------------------------------------------
+def generate_rays(c2w, width: int, height: int, focal: float, near: float, far: float, row0: int = 0, row1=None, device='cuda'):
+    """Rays of the pixel rows [row0,row1) of one pinhole camera as a `utils.Rays` tuple of CUDA tensors
+    (obbpose_dataset.py:613-661; [n,3] x3 and [n,1] x4 like the reference's flattened BoxRays)."""
+    import numpy as np
+    from .utils import Rays
+    row1 = height if row1 is None else row1
+    n = (row1 - row0) * width
+    cam = L.Camera(width=width, height=height, focal=float(focal), near=float(near), far=float(far))
+    flat = np.asarray(c2w, np.float32)[:3, :4].reshape(-1)
+    for i in range(12):
+        cam.c2w[i] = float(flat[i])
+    v3 = [torch.empty(n, 3, device=device) for _ in range(3)]
+    v1 = [torch.empty(n, 1, device=device) for _ in range(4)]
+    check(L.load().durf_generate_rays(stream_ptr(), C.byref(cam), row0, row1, *[ptr(t) if n else None for t in v3 + v1]),
+          "durf_generate_rays")
+    return Rays(v3[0], v3[1], v3[2], v1[0], v1[1], v1[2], v1[3])
+
+
 # ---- K0 ---------------------------------------------------------------------------------------------
 def aa2matrix(angles: torch.Tensor) -> torch.Tensor:
     angles = f32(angles)

@@ -55,10 +55,11 @@ def pixel_rays(c2w: np.ndarray, px: np.ndarray, py: np.ndarray, width: int = WAY
         return (cam[..., None, :] * c2w[:3, :3]).sum(axis=-1).astype(np.float32)
 
     d = world_dir(px, py)
-    # neighbour along y; the last row reuses the previous row's spacing (obbpose_dataset.py:640-643)
-    y0 = np.where(py >= height - 1, py - 1, py)
+    # neighbour along y; the last row gets v[-2:-1] of the (H-1)-row difference array, i.e. |dir(H-3) - dir(H-2)|
+    # (obbpose_dataset.py:640-643)
+    y0 = np.where(py >= height - 1, py - 2, py)
     dn = np.sqrt(((world_dir(px, y0) - world_dir(px, y0 + 1)) ** 2).sum(-1))
-    radii = (dn[..., None] * 2 / np.sqrt(12)).astype(np.float32)
+    radii = ((dn[..., None] * np.float32(2)) / np.float32(np.sqrt(12))).astype(np.float32)   # float32 like the reference's numpy 1.x
     o = np.broadcast_to(c2w[:3, -1], d.shape).astype(np.float32).copy()
     v = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
     ones = np.ones_like(radii)

@@ -94,6 +94,19 @@ int durf_obb_frontend_bwd(durf_stream_t stream, int32_t B, int32_t K,
 int durf_compact_hits(durf_stream_t stream, int32_t B, int32_t K, int32_t k, const int32_t* hit,
                       int32_t* ray_index, int32_t* count);
 
+/* ---- N2: pinhole ray generation ------------------------------------------------------------ */
+typedef struct DurfCamera {
+  int32_t width, height;   /* pixels */
+  float focal;             /* pixels */
+  float c2w[12];           /* camera-to-world [3,4], row-major (HOST values) */
+  float near, far;
+} DurfCamera;
+/* Carla/Waymo._generate_rays_multi (internal/obbpose_dataset.py:613-661) for the pixel rows [row0,row1) of one camera,
+ * row-major: origins, directions (un-normalised), viewdirs [n,3]; radii, lossmult (=1), near, far [n]; n = (row1-row0)*width.
+ * `cam` is a HOST pointer (read during the call). */
+int durf_generate_rays(durf_stream_t stream, const DurfCamera* cam, int32_t row0, int32_t row1, float* origins,
+                       float* directions, float* viewdirs, float* radii, float* lossmult, float* near, float* far);
+
 /* ---- K1: ray-march (sample -> conical frustum Gaussian -> contraction -> IPE) ------------- */
 #define DURF_RM_SAMPLE        (1u << 0)  /* generate t_vals from near/far (mip.sample_along_rays, mip.py:351-368) */
 #define DURF_RM_RANDOMIZED    (1u << 1)  /* stratified jitter with the explicit t_rand buffer (mip.py:360-365) */

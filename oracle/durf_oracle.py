@@ -768,3 +768,25 @@ def adam_step(params: Sequence[Tensor], grads: Sequence[Tensor], m: Sequence[Ten
         denom = torch.sqrt(v2 / (1.0 - beta2 ** t)) + eps
         outp.append(p - lr * mhat / denom); outm.append(m2); outv.append(v2)
     return outp, outm, outv
+
+
+# --------------------------------------------------------------------------------------
+# internal/obbpose_dataset.py : pinhole ray generation (numpy on the host in the reference)
+# --------------------------------------------------------------------------------------
+
+def generate_rays(c2w: np.ndarray, w: int, h: int, focal: float, near: float, far: float):
+    """reference internal/obbpose_dataset.py:613-661 (`_generate_rays_multi`) for one camera, in float32 like the
+    reference's arrays (numpy 1.x value-based casting keeps `v * 2 / np.sqrt(12)` in float32).
+    Returns Rays of numpy arrays shaped [h, w, 3] / [h, w, 1]."""
+    f32 = np.float32
+    c2w = np.asarray(c2w, f32)
+    x, y = np.meshgrid(np.arange(w, dtype=f32), np.arange(h, dtype=f32), indexing='xy')
+    cam_dirs = np.stack([(x - f32(w) * f32(0.5)) / f32(focal), -(y - f32(h) * f32(0.5)) / f32(focal), -np.ones_like(x)], axis=-1)
+    directions = (cam_dirs[..., None, :] * c2w[:3, :3]).sum(axis=-1).astype(f32)
+    origins = np.broadcast_to(c2w[:3, -1], directions.shape).astype(f32)
+    viewdirs = (directions / np.linalg.norm(directions, axis=-1, keepdims=True)).astype(f32)
+    dx = np.sqrt(np.sum((directions[:-1, :, :] - directions[1:, :, :]) ** 2, -1))
+    dx = np.concatenate([dx, dx[-2:-1, :]], 0)
+    radii = ((dx[..., None] * f32(2)) / f32(np.sqrt(12))).astype(f32)
+    ones = np.ones_like(origins[..., :1])
+    return Rays(origins, directions, viewdirs, radii, ones, f32(near) * ones, f32(far) * ones)

@@ -354,3 +354,21 @@ def test_mlp_tensor_core_backward(topo, M):
                 cos = float((got * want).sum() / (got.norm() * want.norm() + 1e-30))
                 rel = float((got - want).norm() / (want.norm() + 1e-30))
                 assert cos >= min_cos and rel <= max_rel, f"{what} vs {tag}: cosine {cos:.5f}, rel Frobenius {rel:.3e}"
+
+
+def test_generate_rays_matches_oracle_bit_exact():
+    """Device ray generation vs the numpy restatement of _generate_rays_multi: float32 arithmetic in the same order, so the
+    comparison is bit-exact (division and sqrt are IEEE, FMA contraction is off)."""
+    ops = _ops()
+    from durf_b200 import synthetic as S
+    rng = np.random.default_rng(5)
+    for (w, h, f) in ((97, 33, 120.25), (1920, 64, 2058.72)):
+        c2w = S.random_c2w(rng)
+        want = O.generate_rays(c2w, w, h, f, 0.5, 200.0)
+        got = ops.generate_rays(c2w, w, h, f, 0.5, 200.0)
+        for a, b, name in zip(got, want, O.Rays._fields):
+            assert torch.equal(a.cpu().reshape(-1), torch.from_numpy(np.ascontiguousarray(b)).reshape(-1)), name
+        part = ops.generate_rays(c2w, w, h, f, 0.5, 200.0, row0=h - 3, row1=h)       # a row range incl. the last row
+        assert torch.equal(part.radii.cpu().reshape(-1), torch.from_numpy(want.radii[h - 3:]).reshape(-1))
+    empty = ops.generate_rays(c2w, 8, 8, 10.0, 0.0, 1.0, row0=4, row1=4)
+    assert empty.origins.shape[0] == 0

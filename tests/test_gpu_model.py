@@ -242,3 +242,22 @@ def test_pose_optimisation_with_tensor_core_background():
     assert float(g64.norm()) > 0
     cos = float(got @ g64 / (got.norm() * g64.norm()))
     assert cos >= 0.98, f"d box_centers cosine {cos:.4f}"
+
+
+def test_render_camera_equals_render_image_on_host_rays():
+    """Device-generated rays give the very same frame as render_image fed the oracle's host rays (bit-exact rays in,
+    same kernels after)."""
+    from durf_b200.obbpose_model import render_camera, render_image
+    from durf_b200 import synthetic as S
+    from durf_b200.utils import Rays
+    sc = H.scene(B=8, K=2, seed=3, behind=True)
+    model = _model(precision='fp32', dynamics=False)
+    v = H.cuda_variables(sc, model)
+    ext = torch.from_numpy(sc['ext']).cuda()
+    w, h, f = 48, 20, 60.0
+    fn = lambda rng, b: model.apply(v, rng, b['rays'], None, b['ext'], b['ts'], False, False, False, b['alpha'])
+    host = O.generate_rays(sc['c2w'], w, h, f, 0.0, 40.0)
+    a = render_image(fn, Rays(*[torch.from_numpy(np.ascontiguousarray(x)) for x in host]), None, ext, 0, None, 10.0, chunk=256)
+    b = render_camera(fn, sc['c2w'], w, h, f, 0.0, 40.0, None, ext, 0, None, 10.0, chunk=256)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)

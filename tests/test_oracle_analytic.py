@@ -155,3 +155,17 @@ def test_adam_and_grad_postprocess():
     np.testing.assert_allclose(gs[0].numpy(), (want * min(1.0, 1.0 / (1e-7 + float(n)))).numpy(), rtol=1e-6)
     p, m, v = O.adam_step([torch.ones(3)], [torch.full((3,), 0.1)], [torch.zeros(3)], [torch.zeros(3)], step=0, lr=1e-3)
     np.testing.assert_allclose(p[0].numpy(), np.full(3, 1 - 1e-3), rtol=1e-5)
+
+
+def test_ray_generation_oracle_matches_synthetic_frame_rays():
+    """oracle.generate_rays (obbpose_dataset.py:613-661) and the benchmark's synthetic.frame_rays are the same rays."""
+    from durf_b200 import synthetic as S
+    rng = np.random.default_rng(3)
+    c2w = S.random_c2w(rng)
+    want = O.generate_rays(c2w, 96, 40, 103.5, 0.0, 40.0)
+    got = S.frame_rays(c2w, width=96, height=40, focal=103.5, far=40.0)
+    for a, b, name in zip(got, want, O.Rays._fields):
+        assert np.array_equal(np.asarray(a).reshape(-1), np.asarray(b).reshape(-1)), name
+    assert float(np.abs(np.linalg.norm(want.viewdirs, axis=-1) - 1).max()) < 1e-6
+    # quirk kept: `np.concatenate([v, v[-2:-1]])` gives the last image row the spacing of row H-3, not H-2 (:643)
+    assert np.array_equal(want.radii[-1], want.radii[-3])
