@@ -99,6 +99,73 @@ resample_kernel(const ResampleParams p) {
   }
 }
 
+// Specialisation for the model's shape (N = 128 bins -> 129 samples): every lane owns 4 consecutive bins, all loops have
+// fixed trip counts and the interval search is a branch-free 7-step bisection, ~3x fewer instructions than the generic
+// kernel above (which stays for other N, e.g. math.sorted_piecewise_constant_pdf on arbitrary histograms).
+__global__ void __launch_bounds__(128)
+resample128_kernel(const ResampleParams p) {
+  __shared__ float s_all[4][2 * 129 + 2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * 4 + warp;
+  if (ray >= p.B) return;
+  constexpr int N = 128, S = 129;
+  float* s_bins = s_all[warp];
+  float* s_cdf = s_bins + S;
+  const float* tv = p.t_vals + (size_t)ray * S;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s_bins[lane + 32 * k] = tv[lane + 32 * k];      // coalesced: 128 contiguous bytes per instruction
+  if (lane == 0) s_bins[N] = tv[N];
+  const float4 w4 = *reinterpret_cast<const float4*>(p.weights + (size_t)ray * N + 4 * lane);
+  float w[4] = {w4.x, w4.y, w4.z, w4.w};
+  float wb[4];
+  if (p.blur) {
+    // blur-pool (mip.py:394-401) on the edge-padded row: neighbours across lanes by shuffle
+    float wl = __shfl_up_sync(kFull, w[3], 1), wr = __shfl_down_sync(kFull, w[0], 1);
+    if (lane == 0) wl = w[0];
+    if (lane == 31) wr = w[3];
+    const float e[6] = {wl, w[0], w[1], w[2], w[3], wr};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wb[k] = 0.5f * (fmaxf(e[k], e[k + 1]) + fmaxf(e[k + 1], e[k + 2])) + p.padding;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wb[k] = w[k];
+  }
+  // math.py:237-245
+  float wsum = warp_sum((wb[0] + wb[1]) + (wb[2] + wb[3]));
+  const float pad = fmaxf(0.f, 1e-5f - wsum);
+  wsum += pad;
+  float pdf[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) pdf[k] = (wb[k] + pad / (float)N) / wsum;
+  // cdf = [0, min(1, cumsum(pdf[:-1])), 1] (math.py:246-251)
+  float acc = warp_scan_excl((pdf[0] + pdf[1]) + (pdf[2] + pdf[3]), lane);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    acc += pdf[k];
+    if (4 * lane + k + 1 < N) s_cdf[4 * lane + k + 1] = fminf(1.f, acc);
+  }
+  if (lane == 0) { s_cdf[0] = 0.f; s_cdf[N] = 1.f; }
+  __syncwarp();
+  float* out = p.out + (size_t)ray * S;
+  const float* ur = p.u_rand ? p.u_rand + (size_t)ray * S : nullptr;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int i = lane + 32 * k;                    // strided ownership: loads of u_rand and stores of the samples coalesce
+    if (k == 4 && lane != 0) break;                 // the 129th sample goes to lane 0
+    float u;
+    if (ur) u = fminf((float)i * p.s_step + ur[i] * p.s_jit, p.u_max);
+    else u = (i == S - 1) ? p.u_max : p.u_max * ((float)i / (float)(S - 1));
+    // last knot j in [0,127] with cdf[j] <= u (cdf[0] = 0 <= u, cdf[128] = 1 > u): branch-free bisection
+    int j = 0;
+#pragma unroll
+    for (int step = 64; step >= 1; step >>= 1) j += (s_cdf[j + step] <= u) ? step : 0;
+    const float c0 = s_cdf[j], c1 = s_cdf[j + 1], b0 = s_bins[j], b1 = s_bins[j + 1];
+    float t = nan_to_num((u - c0) / (c1 - c0));
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    out[i] = b0 + t * (b1 - b0);
+  }
+}
+
 }  // namespace durf
 
 using namespace durf;
@@ -118,8 +185,12 @@ extern "C" int durf_resample_fwd(durf_stream_t stream, int32_t B, int32_t N, con
   p.s_jit = (float)(s - eps32);
   p.u_max = (float)(1.0 - eps32);
   p.out = new_t_vals;
-  const size_t smem = 4 * (3 * (N + 1) + 1) * sizeof(float);
-  resample_kernel<<<ceil_div(B, 4), 128, smem, (cudaStream_t)stream>>>(p);
+  if (N == 128 && num_samples == 129) {
+    resample128_kernel<<<ceil_div(B, 4), 128, 0, (cudaStream_t)stream>>>(p);
+  } else {
+    const size_t smem = 4 * (3 * (N + 1) + 1) * sizeof(float);
+    resample_kernel<<<ceil_div(B, 4), 128, smem, (cudaStream_t)stream>>>(p);
+  }
   DURF_CHECK_LAUNCH("durf_resample_fwd");
   return DURF_OK;
 }
