@@ -97,13 +97,14 @@ __device__ __forceinline__ void epi_pack(const uint32_t (&v)[32], const float4 (
   }
 }
 
-template <int W>
+template <int W, bool SAVE>
 struct TcCfg {
   static constexpr int NHALF = W / 128;                   // N-halves per trunk layer (every tcgen05.mma is M=128, N=128)
   static constexpr int KB = W / 64;                       // 64-wide K blocks of an activation row
   static constexpr int CPW = 64;                          // columns one epilogue warp owns inside a half
   static constexpr int STAGE_BYTES = KB * kBlockBytes;    // one ring stage holds the weights of one (layer, N-half)
-  static constexpr int STAGES = (W == 256) ? 3 : 6;
+  // training (SAVE): one ring stage less, 64 KB of per-warp staging for the asynchronous bulk stores of the activations
+  static constexpr int STAGES = SAVE ? ((W == 256) ? 2 : 4) : ((W == 256) ? 3 : 6);
   static constexpr int TMEM_COLS = 2 * W;                 // W accumulator columns + 2 x W/2 activation columns
   static constexpr int ACC_COL = 0;
   static constexpr int ACT_COL = W;                       // buffer b at ACT_COL + b * W/2 (bf16 pairs)
@@ -111,7 +112,9 @@ struct TcCfg {
   // shared memory map (bytes, from a 1024-aligned base)
   static constexpr int OFF_INP = 0;
   static constexpr int OFF_RING = OFF_INP + kInpBytes;
-  static constexpr int OFF_BIAS = OFF_RING + STAGES * STAGE_BYTES;    // fp32 [MAX_BIAS_LAYERS][W]
+  static constexpr int OFF_STG = OFF_RING + STAGES * STAGE_BYTES;     // [2 buffers][8 epilogue warps][4 KB]
+  static constexpr int STG_BYTES = SAVE ? 2 * 8 * 4096 : 0;
+  static constexpr int OFF_BIAS = OFF_STG + STG_BYTES;                // fp32 [MAX_BIAS_LAYERS][W]
   static constexpr int OFF_WDEN = OFF_BIAS + MAX_BIAS_LAYERS * W * 4; // fp32 [W]
   static constexpr int OFF_WRGB = OFF_WDEN + W * 4;                   // fp32 [3][128]
   static constexpr int OFF_VBIAS = OFF_WRGB + 3 * 128 * 4;            // fp32 [128]
@@ -122,10 +125,10 @@ struct TcCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-template <int W>
+template <int W, bool SAVE>
 __global__ void __launch_bounds__(384, 1)
 mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
-  using C = TcCfg<W>;
+  using C = TcCfg<W, SAVE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -274,6 +277,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     // (the ring lets the issuer run three chunks ahead) and miss a phase.
     const bool releaser = threadIdx.x == 128;
     uint32_t rel_stage = 0;
+    uint32_t stg_buf = 0;                         // SAVE: which of this warp's two 4 KB staging pieces the next epilogue fills
     const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 128;
     long long e_acc = 0, e_ld = 0, e_math = 0, e_st = 0, e_begin = clock64(), eq = 0, e_m0 = 0, e_ld1 = 0, e_m1 = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -325,16 +329,31 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
               else epi_pack<2>(v[i], b4, wden_addr, den, pk);
               tmem_st16(o_buf + (col0 + i * 32) / 2, pk);
               if (tr) { if (i == 0) e_m0 += clock64() - tq1; else e_m1 += clock64() - tq1; }
-              if (p.saved) {      // training: keep the activation (the A operand of wgrad, the ReLU mask of dgrad)
-                const int cc = col0 + i * 32;
-                uint8_t* blk = p.saved + ((size_t)tile * p.saved_blocks_per_tile + g * C::KB + (cc >> 6)) * kBlockBytes;
-#pragma unroll
-                for (int q2 = 0; q2 < 2; ++q2) {
-                  const uint32_t w8[8] = {pk[8 * q2], pk[8 * q2 + 1], pk[8 * q2 + 2], pk[8 * q2 + 3], pk[8 * q2 + 4], pk[8 * q2 + 5],
-                                          pk[8 * q2 + 6], pk[8 * q2 + 7]};
-                  st_sw128_pair(blk, (uint32_t)row, ((cc & 63) >> 3) + 2 * q2, w8);
+              if constexpr (SAVE) {
+                // training: keep the activation (A operand of wgrad, ReLU mask of dgrad).  The warp's 32 rows x 64 columns
+                // are a contiguous 4 KB piece of the global block image: stage it in shared memory in image order ...
+                if (i == 0) {
+                  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the piece filled two epilogues ago was read
+                  __syncwarp();
                 }
+                const uint32_t sdst = sbase + C::OFF_STG + ((stg_buf * 8 + (warp - 4)) << 12) + (lane >> 3) * 1024 + (lane & 7) * 128;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + (((uint32_t)(i * 4 + q4) ^ (lane & 7)) << 4)),
+                               "r"(pk[4 * q4]), "r"(pk[4 * q4 + 1]), "r"(pk[4 * q4 + 2]), "r"(pk[4 * q4 + 3]) : "memory");
               }
+            }
+            if constexpr (SAVE) {
+              // ... and hand it to the bulk-copy engine: the store to HBM never blocks the epilogue
+              __syncwarp();
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              if (lane == 0) {
+                uint8_t* gdst = p.saved + ((size_t)tile * p.saved_blocks_per_tile + g * C::KB + (col0 >> 6)) * kBlockBytes + q * 4096;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(gdst),
+                             "r"(sbase + C::OFF_STG + ((stg_buf * 8 + (warp - 4)) << 12)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+              stg_buf ^= 1;
             }
             if (tr) { e_math += clock64() - eq; eq = clock64(); }
             tmem_st_wait();
@@ -363,7 +382,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
                 rgb[0] = fmaf(a0, w0.x, rgb[0]); rgb[0] = fmaf(a1, w0.y, rgb[0]); rgb[0] = fmaf(a2, w0.z, rgb[0]); rgb[0] = fmaf(a3, w0.w, rgb[0]);
                 rgb[1] = fmaf(a0, w1.x, rgb[1]); rgb[1] = fmaf(a1, w1.y, rgb[1]); rgb[1] = fmaf(a2, w1.z, rgb[1]); rgb[1] = fmaf(a3, w1.w, rgb[1]);
                 rgb[2] = fmaf(a0, w2.x, rgb[2]); rgb[2] = fmaf(a1, w2.y, rgb[2]); rgb[2] = fmaf(a2, w2.z, rgb[2]); rgb[2] = fmaf(a3, w2.w, rgb[2]);
-                if (p.saved) {
+                if (SAVE) {
                   const int cc = col0 + c;
                   uint8_t* blk = p.saved + ((size_t)tile * p.saved_blocks_per_tile + g * C::KB + (cc >> 6)) * kBlockBytes;
                   *reinterpret_cast<uint2*>(blk + sw128_offset(row, (cc & 63) >> 3) + (cc & 7) * 2) =
@@ -397,6 +416,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       }
     }
   }
+  if (SAVE && warp >= 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staged activations are in HBM
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -583,16 +603,19 @@ int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.M < sms ? a.M : sms;
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
+  auto launch = [&](auto kernel, int smem) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) kernel<<<grid, 384, smem, st>>>(P);
+  };
   if (t.width == 256) {
-    e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
-    DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_fwd(bf16): smem attribute: %s", cudaGetErrorString(e));
-    mlp_tc_fwd_kernel<256><<<grid, 384, TcCfg<256>::SMEM_BYTES, st>>>(P);
+    if (P.saved) launch(mlp_tc_fwd_kernel<256, true>, TcCfg<256, true>::SMEM_BYTES);
+    else launch(mlp_tc_fwd_kernel<256, false>, TcCfg<256, false>::SMEM_BYTES);
   } else {
-    e = cudaFuncSetAttribute(mlp_tc_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
-    DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_fwd(bf16): smem attribute: %s", cudaGetErrorString(e));
-    mlp_tc_fwd_kernel<128><<<grid, 384, TcCfg<128>::SMEM_BYTES, st>>>(P);
+    if (P.saved) launch(mlp_tc_fwd_kernel<128, true>, TcCfg<128, true>::SMEM_BYTES);
+    else launch(mlp_tc_fwd_kernel<128, false>, TcCfg<128, false>::SMEM_BYTES);
   }
+  DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_fwd(bf16): smem attribute: %s", cudaGetErrorString(e));
   DURF_CHECK_LAUNCH("durf_mlp_fwd(bf16)");
   return DURF_OK;
 }

@@ -47,15 +47,17 @@ template <int W>
 struct DgCfg {
   static constexpr int KB = W / 64;
   static constexpr int STAGE_BYTES = KB * kBlockBytes;
-  static constexpr int STAGES = (W == 256) ? 3 : 6;
+  static constexpr int STAGES = (W == 256) ? 2 : 4;
   static constexpr int TMEM_COLS = 2 * W;
   static constexpr int ACC_COL = 0;
   static constexpr int ACT_COL = W;
   static constexpr int OFF_RING = 0;
-  static constexpr int OFF_WDEN = OFF_RING + STAGES * STAGE_BYTES;    // fp32 [W]
+  static constexpr int OFF_OUT = OFF_RING + STAGES * STAGE_BYTES;     // [8 epilogue warps][4 KB] dZ pieces staged for bulk stores
+  static constexpr int OFF_MSK = OFF_OUT + 8 * 4096;                  // [8 epilogue warps][4 KB] activation pieces (ReLU masks), bulk-loaded
+  static constexpr int OFF_WDEN = OFF_MSK + 8 * 4096;                 // fp32 [W]
   static constexpr int OFF_WRGB = OFF_WDEN + W * 4;                   // fp32 [128][4] (rgb head kernel rows, padded)
   static constexpr int OFF_MISC = OFF_WRGB + 128 * 4 * 4;
-  static constexpr int MISC_BYTES = 256;
+  static constexpr int MISC_BYTES = 512;
   static constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -64,7 +66,7 @@ struct DgCfg {
 // so the unrolled body is branch-free.  Writes the group's 64 bytes of the dZ tile image row and returns the packed words.
 template <int KIND>
 __device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], const uint4 (&m4)[4], float gden, uint32_t wden_addr,
-                                        uint8_t* __restrict__ out_row_base, int row, int chunk0, uint32_t (&pk)[16]);
+                                        uint32_t stage_row, uint32_t r7, int chunk0, uint32_t (&pk)[16]);
 
 // keep a packed bf16 pair where the matching activation halfwords are non-zero (ReLU outputs are +0 or positive)
 __device__ __forceinline__ uint32_t mask_pair(uint32_t packed, uint32_t act) {
@@ -74,7 +76,7 @@ __device__ __forceinline__ uint32_t mask_pair(uint32_t packed, uint32_t act) {
 
 template <int KIND>
 __device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], const uint4 (&m4)[4], float gden, uint32_t wden_addr,
-                                        uint8_t* __restrict__ out_blk, int row, int chunk0, uint32_t (&pk)[16]) {
+                                        uint32_t stage_row, uint32_t r7, int chunk0, uint32_t (&pk)[16]) {
 #pragma unroll
   for (int c8 = 0; c8 < 4; ++c8) {
     const uint32_t aw[4] = {m4[c8].x, m4[c8].y, m4[c8].z, m4[c8].w};
@@ -90,12 +92,11 @@ __device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], const uint4 (&m
       pk[c8 * 4 + e] = pr;
     }
   }
+  // the row's 64 bytes go to the warp's staging piece (image order), from where one bulk store takes them to HBM
 #pragma unroll
-  for (int q2 = 0; q2 < 2; ++q2) {
-    const uint32_t w8[8] = {pk[8 * q2], pk[8 * q2 + 1], pk[8 * q2 + 2], pk[8 * q2 + 3], pk[8 * q2 + 4], pk[8 * q2 + 5], pk[8 * q2 + 6],
-                            pk[8 * q2 + 7]};
-    st_sw128_pair(out_blk, (uint32_t)row, chunk0 + 2 * q2, w8);
-  }
+  for (int q4 = 0; q4 < 4; ++q4)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (((uint32_t)(chunk0 + q4) ^ r7) << 4)), "r"(pk[4 * q4]),
+                 "r"(pk[4 * q4 + 1]), "r"(pk[4 * q4 + 2]), "r"(pk[4 * q4 + 3]) : "memory");
 }
 
 template <int W>
@@ -115,12 +116,14 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
   auto bar_acc_full = [&](int h) { return bar0 + 8 * (16 + h); };
   auto bar_a_ready = [&](int h) { return bar0 + 8 * (18 + h); };
   const uint32_t bar_p_ready = bar0 + 8 * 20;
-  static_assert(16 + 8 * 21 <= C::MISC_BYTES, "barrier area");
+  auto bar_mask = [&](int w) { return bar0 + 8 * (21 + w); };      // one per epilogue warp: its mask piece has landed
+  static_assert(16 + 8 * 29 <= C::MISC_BYTES, "barrier area");
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int h = 0; h < 2; ++h) { mbar_init(bar_acc_full(h), 1); mbar_init(bar_a_ready(h), 256); }
     mbar_init(bar_p_ready, 256);
+    for (int w = 0; w < 8; ++w) mbar_init(bar_mask(w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -200,7 +203,7 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
     const int q = warp & 3, ch = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t af_par[2] = {0, 0};
+    uint32_t af_par[2] = {0, 0}, msk_par = 0;
     const bool releaser = threadIdx.x == 128;     // an active participant frees the ring stages (see mlp_tc.cu)
     uint32_t rel_stage = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -238,46 +241,70 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
         mbar_arrive(bar_p_ready);
       }
       const float gden = p.d_raw_density[(size_t)ray * kTileM + row];
+      const uint32_t my_out = sbase + C::OFF_OUT + ((warp - 4) << 12), my_msk = sbase + C::OFF_MSK + ((warp - 4) << 12);
+      const uint32_t row_off = (lane >> 3) * 1024 + (lane & 7) * 128, r7 = lane & 7;
+      // the warp's 32 rows x 64 columns of a block image are a contiguous 4 KB piece: masks arrive by one bulk load per
+      // epilogue (issued one epilogue ahead), dZ leaves by one bulk store, so HBM traffic never blocks the epilogue
+      auto issue_mask = [&](int s2, int h2) {
+        if (lane == 0) {
+          const uint8_t* src = sv + (size_t)(p.st[s2].mask_slot + 2 * h2 + ch) * kBlockBytes + q * 4096;
+          mbar_arrive_expect_tx(bar_mask(warp - 4), 4096);
+          bulk_g2s(my_msk, src, 4096, bar_mask(warp - 4));
+        }
+      };
       for (int s = 0; s < p.n_stages; ++s) {
         const DgStage S = p.st[s];
         const uint32_t o_buf = t_lane + C::ACT_COL + ((s + 1) & 1) * (W / 2);
         const bool feeds_next = s + 1 < p.n_stages;
         for (int h = 0; h < S.n_halves; ++h) {
           const int col0 = h * 128 + ch * 64;
-          // the mask rows of this thread's 64 columns: one 128-byte line of the saved activation block
-          const uint8_t* act = sv + (size_t)(S.mask_slot + (col0 >> 6)) * kBlockBytes;
-          uint4 m4[4];
-          if (S.kind != 0) {
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) m4[c8] = *reinterpret_cast<const uint4*>(act + sw128_offset(row, c8));
-          }
           mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
           if (releaser) { mbar_arrive(bar_empty(rel_stage)); if (++rel_stage == C::STAGES) rel_stage = 0; }
           tc_fence_after();
-          uint8_t* out = dzt + (size_t)(S.out_slot + (col0 >> 6)) * kBlockBytes;
+          uint32_t v[32];
+          tmem_ld32_issue(t_lane + C::ACC_COL + col0, v);
+          if (S.kind != 0) { mbar_wait(bar_mask(warp - 4), msk_par); msk_par ^= 1; }
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // previous dZ piece was read out
+          __syncwarp();
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            uint32_t v[32];
-            tmem_ld32_issue(t_lane + C::ACC_COL + col0 + i * 32, v);
+            uint4 m4[4];
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              if (S.kind != 0) {
+                const float4 f = lds128_volatile(my_msk + row_off + (((uint32_t)(i * 4 + c8) ^ r7) << 4));
+                m4[c8] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
+              } else {
+                m4[c8] = make_uint4(~0u, ~0u, ~0u, ~0u);
+              }
+            }
             tmem_ld_wait();
             tmem_ld_pin(v);
             uint32_t pk[16];
             const uint32_t wden_addr = sbase + C::OFF_WDEN + (col0 + i * 32) * 4;
-            if (S.kind == 0) dg_pack<0>(v, m4, gden, wden_addr, out, row, i * 4, pk);
-            else if (S.kind == 1) dg_pack<1>(v, m4, gden, wden_addr, out, row, i * 4, pk);
-            else dg_pack<2>(v, m4, gden, wden_addr, out, row, i * 4, pk);
-            if (i == 0 && S.kind != 0) {       // mask rows of the second 32-column group
-#pragma unroll
-              for (int c8 = 0; c8 < 4; ++c8) m4[c8] = *reinterpret_cast<const uint4*>(act + sw128_offset(row, 4 + c8));
-            }
+            if (S.kind == 0) dg_pack<0>(v, m4, gden, wden_addr, my_out + row_off, r7, i * 4, pk);
+            else if (S.kind == 1) dg_pack<1>(v, m4, gden, wden_addr, my_out + row_off, r7, i * 4, pk);
+            else dg_pack<2>(v, m4, gden, wden_addr, my_out + row_off, r7, i * 4, pk);
+            if (i == 0) tmem_ld32_issue(t_lane + C::ACC_COL + col0 + 32, v);
             if (feeds_next) tmem_st16(o_buf + (col0 + i * 32) / 2, pk);
           }
           if (feeds_next) tmem_st_wait();
           tc_fence_before();
           mbar_arrive(bar_a_ready(h));     // next stage's A operand half is in TMEM (last stage: accumulators drained)
+          // off the critical path: publish the dZ piece, fetch the next epilogue's mask piece
+          __syncwarp();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (lane == 0) {
+            uint8_t* gdst = dzt + (size_t)(S.out_slot + (col0 >> 6)) * kBlockBytes + q * 4096;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(gdst), "r"(my_out) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          const int h2 = (h + 1 < S.n_halves) ? h + 1 : 0, s2 = (h + 1 < S.n_halves) ? s : s + 1;
+          if (s2 < p.n_stages && p.st[s2].kind != 0) issue_mask(s2, h2);
         }
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every staged dZ piece is in HBM
   }
   tc_fence_before();
   __syncthreads();
