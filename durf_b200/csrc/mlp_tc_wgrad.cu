@@ -335,7 +335,9 @@ int mlp_tc_wgrad_launch(cudaStream_t st, const DurfMlpTopology& t, int saved_blo
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = P.M < sms ? P.M : sms;
+  // every CTA ends each job with a [in,out] fp32 reduction into the global gradient: with few tiles use fewer CTAs
+  int grid = (P.M + 15) / 16;
+  grid = grid < 1 ? 1 : (grid > sms ? sms : grid);
   cudaError_t e = cudaFuncSetAttribute(mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
   DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_bwd(bf16): smem attribute: %s", cudaGetErrorString(e));
   mlp_tc_wgrad_kernel<<<grid, 384, kWgSmemBytes, st>>>(P);
