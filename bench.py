@@ -202,7 +202,8 @@ def train_bench(dev, rank, world, steps, warmup, precision):
     mlp = S.glorot_mlp(rng_w, 60, 256, 0.0)
     box_mlps = [S.glorot_mlp(rng_w, 63, 128, 0.0) for _ in range(K)]
     tg = S.targets(rng, B)
-    model = MipNerfModel(precision=precision, num_objects=K)
+    pose = os.environ.get("DURF_BENCH_POSE_OPT", "0") == "1"      # C5: joint box-pose optimisation (object MLPs then run in fp32)
+    model = MipNerfModel(precision=precision, num_objects=K, no_pose_opt=not pose, no_yaw_opt=not pose)
     v = Variables.allocate(model, K, centers.shape[0], dev)
     v.load_mlp("MLP_0", mlp)
     for k, m in enumerate(box_mlps):
@@ -224,7 +225,7 @@ def train_bench(dev, rank, world, steps, warmup, precision):
 
     def step_resident():
         nonlocal state
-        state, st = train_step(model, config, rnd_dev, state, resident, lr=5e-4, eps=3.0, alpha=10.0, world_size=world)
+        state, st = train_step(model, config, rnd_dev, state, resident, lr=5e-4, eps=3.0, alpha=4.5 if pose else 10.0, world_size=world)
         return st
 
     def step_e2e():

@@ -33,7 +33,8 @@ bool mlp_tc_bwd_supported(const DurfMlpTopology& t);
 int mlp_tc_saved_blocks(const DurfMlpTopology& t);
 int64_t mlp_tc_packed_t_bytes(const DurfMlpTopology& t);
 int mlp_tc_pack_t(cudaStream_t st, const DurfMlpTopology& t, const float* params, void* packed_t);
-int mlp_tc_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density, float* d_params);
+int mlp_tc_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density, float* d_params,
+                    float* d_features);
 
 }  // namespace durf
 
@@ -112,7 +113,5 @@ extern "C" int durf_mlp_bwd(durf_stream_t stream, const DurfMlpArgs* args, const
   if (args->M == 0) return DURF_OK;
   if (args->precision == DURF_PREC_FP32)
     return mlp_fp32_backward((cudaStream_t)stream, *args, d_raw_rgb, d_raw_density, d_params, d_features);
-  DURF_REQUIRE(d_features == nullptr, DURF_E_UNSUPPORTED,
-               "durf_mlp_bwd(bf16): no input gradient on the tensor-core path (use DURF_PREC_FP32 for the box-pose gradient)");
-  return mlp_tc_backward((cudaStream_t)stream, *args, d_raw_rgb, d_raw_density, d_params);
+  return mlp_tc_backward((cudaStream_t)stream, *args, d_raw_rgb, d_raw_density, d_params, d_features);
 }

@@ -8,8 +8,10 @@
 // stage is issued as N-halves so the masking epilogue of one half overlaps the MMAs of the other, the transposed weight
 // image streams through a 3-stage ring of 64 KB chunks.  Every dZ (and dBott, dZ_cond) is also written to HBM as tile
 // images: they are the B operands of the weight-gradient kernel (mlp_tc_wgrad.cu).  The ReLU masks come from the
-// activations the forward pass saved.  No input gradient is produced (the background branch needs none: its samples
-// depend on no parameter; the object-pose path uses the fp32 kernels).
+// activations the forward pass saved.  For width 128 (BoxMLP) an optional last stage forms the input gradient
+//   dX = dZ_0 W_0^T + dZ_skip W_skip[width:]^T   (64 columns, fp32 rows)
+// that the box-pose path needs; dZ_skip waits in a third TMEM buffer.  The background branch needs no input gradient
+// (its samples depend on no parameter).
 #include "tc_common.cuh"
 #include "mlp_topology.h"
 
@@ -18,12 +20,19 @@ namespace durf {
 constexpr int kDgMaxStages = 12;
 
 struct DgStage {
-  int n_halves;     // output columns / 128
+  int n_halves;     // output columns / 128 (1 for the 64-column input-gradient stage)
   int n_kb;         // 64-wide K blocks of the incoming dZ
-  int kind;         // 0: linear (dBott); 1: + density term, mask; 2: mask
+  int kind;         // 0: linear (dBott); 1: + density term, mask; 2: mask; 3: input gradient (fp32 rows to d_features)
   int mask_slot;    // block offset (inside a saved tile record) of the activation whose sign masks this stage's output
   int out_slot;     // block offset (inside a dz tile record) where this stage's output is stored
   int block0;       // first 16 KB block of this stage inside the transposed weight image
+  int a_sel;        // TMEM buffer holding the A operand: 0 / 1 = the alternating dZ buffers, 2 = the kept dZ of the skip layer
+  int o_sel;        // buffer the epilogue writes the next A operand to (-1: none)
+  int first_part;   // first MMA overwrites the accumulator
+  int last_part;    // commit acc_full after this entry (an epilogue follows); entries with 0 only accumulate
+  int parts;        // ring stages the epilogue releases (entries since the previous epilogue)
+  int to_skip;      // the epilogue also keeps its dZ in the skip buffer (it multiplies the input rows of the skip layer later)
+  int ncols;        // MMA N: 128, or 64 for the input gradient
 };
 
 struct DgParams {
@@ -39,6 +48,8 @@ struct DgParams {
   int n_stages;
   int cond_slot;             // slot of the condition layer (its activation in `saved`, dZ_cond in `dz`)
   int off_wden, off_wrgb;
+  float* d_features;         // [opt] [M*128, in_dim] fp32 gradient w.r.t. the input features (object MLPs, box-pose path)
+  int in_dim;
   int trace;
   DgStage st[kDgMaxStages];
 };
@@ -48,7 +59,7 @@ struct DgCfg {
   static constexpr int KB = W / 64;
   static constexpr int STAGE_BYTES = KB * kBlockBytes;
   static constexpr int STAGES = (W == 256) ? 2 : 4;
-  static constexpr int TMEM_COLS = 2 * W;
+  static constexpr int TMEM_COLS = (W == 128) ? 512 : 2 * W;   // W = 128 also keeps the skip layer's dZ (64 columns at ACT_COL + W)
   static constexpr int ACC_COL = 0;
   static constexpr int ACT_COL = W;
   static constexpr int OFF_RING = 0;
@@ -160,7 +171,7 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp walks the schedule (uniform control flow), one elected lane issues =====
     {
-      constexpr uint32_t idesc = umma_idesc(128, 128);
+      constexpr uint32_t idesc128 = umma_idesc(128, 128), idesc64 = umma_idesc(128, 64);
       constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       uint32_t stage = 0, phase = 0, ar_par[2] = {0, 0}, pr_par = 0;
       int it = 0;
@@ -168,7 +179,8 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it)
         for (int s = 0; s < p.n_stages; ++s) {
           const DgStage S = p.st[s];
-          const uint32_t a_buf = tmem_u + C::ACT_COL + (s & 1) * (W / 2);
+          const uint32_t a_buf = tmem_u + C::ACT_COL + S.a_sel * (W / 2);
+          const uint32_t idesc = S.ncols == 64 ? idesc64 : idesc128;
           for (int nh = 0; nh < S.n_halves; ++nh) {
             const uint32_t d_addr = tmem_u + C::ACC_COL + nh * 128;
             if (s == 0 && nh == 0) {
@@ -183,17 +195,17 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
 #pragma unroll
             for (int kb = 0; kb < C::KB; ++kb) {
               if (kb < S.n_kb) {
-                if (s > 0 && nh == 0 && (kb & 1) == 0) {   // first K block produced by half kb/2 of the previous stage's epilogue
+                if (s > 0 && S.a_sel != 2 && nh == 0 && (kb & 1) == 0) {   // first K block produced by half kb/2 of the previous epilogue
                   mbar_wait(bar_a_ready(kb >> 1), ar_par[kb >> 1]); ar_par[kb >> 1] ^= 1;
                   tc_fence_after();
                 }
 #pragma unroll
                 for (int k16 = 0; k16 < 4; ++k16)
                   umma_ts_conv(d_addr, a_buf + kb * 32 + k16 * 8, b_lo + ((kb * kBlockBytes + k16 * 32) >> 4), desc_hi, idesc,
-                          (kb == 0 && k16 == 0) ? 0u : 1u);
+                          (S.first_part && kb == 0 && k16 == 0) ? 0u : 1u);
               }
             }
-            tc_commit_conv(bar_acc_full(nh));
+            if (S.last_part) tc_commit_conv(bar_acc_full(nh));
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -254,16 +266,33 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
       };
       for (int s = 0; s < p.n_stages; ++s) {
         const DgStage S = p.st[s];
-        const uint32_t o_buf = t_lane + C::ACT_COL + ((s + 1) & 1) * (W / 2);
-        const bool feeds_next = s + 1 < p.n_stages;
+        if (!S.last_part) continue;                    // entries that only accumulate have no epilogue
+        const uint32_t o_buf = t_lane + C::ACT_COL + (S.o_sel < 0 ? 0 : S.o_sel) * (W / 2);
+        const bool feeds_next = S.o_sel >= 0;
+        const bool masked = S.kind == 1 || S.kind == 2;
         for (int h = 0; h < S.n_halves; ++h) {
           const int col0 = h * 128 + ch * 64;
           mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
-          if (releaser) { mbar_arrive(bar_empty(rel_stage)); if (++rel_stage == C::STAGES) rel_stage = 0; }
+          if (releaser)
+            for (int r = 0; r < S.parts; ++r) { mbar_arrive(bar_empty(rel_stage)); if (++rel_stage == C::STAGES) rel_stage = 0; }
           tc_fence_after();
+          if (S.kind == 3) {
+            // input gradient: 64 accumulator columns (the in_dim features), fp32 rows straight to d_features
+            uint32_t v[32];
+            tmem_ld32_issue(t_lane + C::ACC_COL + ch * 32, v);
+            tmem_ld_wait();
+            tmem_ld_pin(v);
+            tc_fence_before();
+            mbar_arrive(bar_a_ready(0));               // accumulators drained
+            float* dx = p.d_features + ((size_t)tile * kTileM + row) * p.in_dim;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (ch * 32 + e < p.in_dim) dx[ch * 32 + e] = __uint_as_float(v[e]);
+            continue;
+          }
           uint32_t v[32];
           tmem_ld32_issue(t_lane + C::ACC_COL + col0, v);
-          if (S.kind != 0) { mbar_wait(bar_mask(warp - 4), msk_par); msk_par ^= 1; }
+          if (masked) { mbar_wait(bar_mask(warp - 4), msk_par); msk_par ^= 1; }
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // previous dZ piece was read out
           __syncwarp();
 #pragma unroll
@@ -271,7 +300,7 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
             uint4 m4[4];
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
-              if (S.kind != 0) {
+              if (masked) {
                 const float4 f = lds128_volatile(my_msk + row_off + (((uint32_t)(i * 4 + c8) ^ r7) << 4));
                 m4[c8] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
               } else {
@@ -287,8 +316,9 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
             else dg_pack<2>(v, m4, gden, wden_addr, my_out + row_off, r7, i * 4, pk);
             if (i == 0) tmem_ld32_issue(t_lane + C::ACC_COL + col0 + 32, v);
             if (feeds_next) tmem_st16(o_buf + (col0 + i * 32) / 2, pk);
+            if (W == 128 && S.to_skip) tmem_st16(t_lane + C::ACT_COL + 2 * (W / 2) + (col0 + i * 32) / 2, pk);
           }
-          if (feeds_next) tmem_st_wait();
+          if (feeds_next || S.to_skip) tmem_st_wait();
           tc_fence_before();
           mbar_arrive(bar_a_ready(h));     // next stage's A operand half is in TMEM (last stage: accumulators drained)
           // off the critical path: publish the dZ piece, fetch the next epilogue's mask piece
@@ -299,8 +329,9 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(gdst), "r"(my_out) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          const int h2 = (h + 1 < S.n_halves) ? h + 1 : 0, s2 = (h + 1 < S.n_halves) ? s : s + 1;
-          if (s2 < p.n_stages && p.st[s2].kind != 0) issue_mask(s2, h2);
+          int h2 = h + 1, s2 = s;
+          if (h2 >= S.n_halves) { h2 = 0; ++s2; while (s2 < p.n_stages && !p.st[s2].last_part) ++s2; }    // next entry with an epilogue
+          if (s2 < p.n_stages && (p.st[s2].kind == 1 || p.st[s2].kind == 2)) issue_mask(s2, h2);
         }
       }
     }
@@ -322,7 +353,8 @@ struct PackTParams {
   const float* params;
   uint8_t* packed;
   int n_blocks;
-  int w_off[kDgMaxBlocks], ld[kDgMaxBlocks], in_first[kDgMaxBlocks], out_first[kDgMaxBlocks], out_avail[kDgMaxBlocks];
+  int w_off[kDgMaxBlocks], ld[kDgMaxBlocks], in_first[kDgMaxBlocks], in_avail[kDgMaxBlocks], out_first[kDgMaxBlocks],
+      out_avail[kDgMaxBlocks];
 };
 __global__ void pack_weights_t_kernel(const __grid_constant__ PackTParams p) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -333,7 +365,8 @@ __global__ void pack_weights_t_kernel(const __grid_constant__ PackTParams p) {
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int k = c * 8 + 2 * e;
-    w[e] = pack_bf16x2(k < p.out_avail[blk] ? src[2 * e] : 0.f, k + 1 < p.out_avail[blk] ? src[2 * e + 1] : 0.f);
+    const bool row_ok = r < p.in_avail[blk];
+    w[e] = pack_bf16x2(row_ok && k < p.out_avail[blk] ? src[2 * e] : 0.f, row_ok && k + 1 < p.out_avail[blk] ? src[2 * e + 1] : 0.f);
   }
   *reinterpret_cast<uint4*>(p.packed + (size_t)blk * kBlockBytes + sw128_offset(r, c)) = make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -345,30 +378,57 @@ bool mlp_tc_bwd_supported(const DurfMlpTopology& t) {
 
 int mlp_tc_saved_blocks(const DurfMlpTopology& t) { return (t.depth + 1) * (t.width / 64) + t.cond_width / 64; }
 
-// stage list + per-block source description; returns the number of blocks of the transposed image
-static int build_dg(const DurfMlpTopology& t, DgParams& P, PackTParams* pp) {
+// stage list + per-block source description; returns the number of blocks of the transposed image.  The image always
+// carries the input-gradient blocks (width 128 only); `want_dx` decides whether the kernel walks those last two entries.
+static int build_dg(const DurfMlpTopology& t, DgParams& P, PackTParams* pp, bool want_dx = false) {
   MlpLayout L(t);
   const int KB = t.width / 64, NH = t.width / 128;
   auto slot = [&](int g) { return g * KB; };
   int ns = 0, blocks = 0;
-  auto add = [&](int layer, int n_kb, int kind, int mask_slot, int out_slot) {
-    DgStage& S = P.st[ns++];
-    S.n_halves = NH; S.n_kb = n_kb; S.kind = kind; S.mask_slot = mask_slot; S.out_slot = out_slot; S.block0 = blocks;
-    for (int nh = 0; nh < NH; ++nh)
+  // entry: `n_out_blocks` x n_kb blocks with block[r][k] = kernel(layer)[in_first + 128 nh + r][64 kb + k]
+  auto add = [&](int layer, int n_kb, int kind, int mask_slot, int out_slot, int in_first = 0, int in_avail = 1 << 30) -> DgStage& {
+    DgStage& S = P.st[ns];
+    S.n_halves = (kind == 3) ? 1 : NH; S.n_kb = n_kb; S.kind = kind; S.mask_slot = mask_slot; S.out_slot = out_slot; S.block0 = blocks;
+    S.a_sel = ns & 1; S.o_sel = (ns + 1) & 1; S.first_part = 1; S.last_part = 1; S.parts = 1; S.to_skip = 0; S.ncols = 128;
+    ++ns;
+    for (int nh = 0; nh < S.n_halves; ++nh)
       for (int kb = 0; kb < n_kb; ++kb, ++blocks)
         if (pp) {
           pp->w_off[blocks] = (int)L.w_off[layer]; pp->ld[blocks] = L.out_dim[layer];
-          pp->in_first[blocks] = nh * 128; pp->out_first[blocks] = kb * 64;
+          pp->in_first[blocks] = in_first + nh * 128;
+          pp->in_avail[blocks] = in_avail - nh * 128 < 128 ? (in_avail - nh * 128 < 0 ? 0 : in_avail - nh * 128) : 128;
+          pp->out_first[blocks] = kb * 64;
           pp->out_avail[blocks] = L.out_dim[layer] - kb * 64 < 64 ? L.out_dim[layer] - kb * 64 : 64;
         }
+    return S;
   };
   // stage 0: dBott = dZ_cond W_cond[:width]^T   (contraction over the 128 condition outputs)
   add(t.depth + 2, t.cond_width / 64, 0, 0, slot(t.depth));
   // stage 1: dZ_{depth-1} = (dBott W_bott^T + d_den (x) w_den) * [a_{depth-1} > 0]
   add(t.depth + 1, KB, 1, slot(t.depth - 1), slot(t.depth - 1));
   // stages 2..: dZ_{g-1} = (dZ_g W_g[:width]^T) * [a_{g-1} > 0]
-  for (int g = t.depth - 1; g >= 1; --g) add(g, KB, 2, slot(g - 1), slot(g - 1));
-  P.n_stages = ns;
+  int skip_layer = -1;                                       // trunk layer whose input is [a_{g-1} | x]
+  for (int g = 1; g < t.depth; ++g)
+    if ((g - 1) % t.skip == 0 && g - 1 > 0) skip_layer = g;
+  for (int g = t.depth - 1; g >= 1; --g) {
+    DgStage& S = add(g, KB, 2, slot(g - 1), slot(g - 1));
+    if (g - 1 == skip_layer) S.to_skip = 1;                  // this stage's output is dZ of the skip layer: keep it
+  }
+  const int n_core = ns;
+  P.st[n_core - 1].o_sel = -1;
+  // input gradient (width 128: the kept dZ fits in TMEM): dX = dZ_0 W_0^T + dZ_skip W_skip[width:]^T, 64 output columns
+  if (t.width == 128) {
+    DgStage& F0 = add(0, KB, 3, 0, 0, 0, t.in_dim);
+    F0.a_sel = n_core & 1; F0.o_sel = -1; F0.last_part = (skip_layer < 0) ? 1 : 0; F0.ncols = 64;
+    if (skip_layer >= 0) {
+      DgStage& F1 = add(skip_layer, KB, 3, 0, 0, t.width, t.in_dim);
+      F1.a_sel = 2; F1.o_sel = -1; F1.first_part = 0; F1.parts = 2; F1.ncols = 64;
+    }
+    if (want_dx) P.st[n_core - 1].o_sel = n_core & 1;        // dZ_0 must reach TMEM as the A operand of the first part
+  }
+  P.n_stages = (want_dx && t.width == 128) ? ns : n_core;
+  if (!want_dx)
+    for (int i = 0; i < n_core; ++i) P.st[i].to_skip = 0;
   P.cond_slot = slot(t.depth + 1);
   P.off_wden = (int)L.w_off[t.depth];
   P.off_wrgb = (int)L.w_off[t.depth + 3];
@@ -395,7 +455,8 @@ int mlp_tc_pack_t(cudaStream_t st, const DurfMlpTopology& t, const float* params
 
 int mlp_tc_dgrad_launch(cudaStream_t st, const DurfMlpTopology& t, const DgParams& base) {
   DgParams P = base;
-  build_dg(t, P, nullptr);
+  build_dg(t, P, nullptr, base.d_features != nullptr);
+  P.d_features = base.d_features; P.in_dim = t.in_dim;
   P.saved_blocks = mlp_tc_saved_blocks(t);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -426,7 +487,10 @@ int mlp_tc_wgrad_run(cudaStream_t st, const DurfMlpTopology& t, const uint8_t* s
                      const float* d_raw_rgb, const float* d_raw_density, const float* cond, const int32_t* ray_index,
                      const int32_t* count, int M, float* d_params);
 
-int mlp_tc_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density, float* d_params) {
+int mlp_tc_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density, float* d_params,
+                    float* d_features) {
+  DURF_REQUIRE(d_features == nullptr || a.topo.width == 128, DURF_E_UNSUPPORTED,
+               "durf_mlp_bwd(bf16): the input gradient is available for width-128 networks (BoxMLP) only");
   const DurfMlpTopology& t = a.topo;
   DURF_REQUIRE(mlp_tc_bwd_supported(t), DURF_E_UNSUPPORTED, "durf_mlp_bwd(bf16): no tensor-core backward for this topology");
   DURF_REQUIRE(a.N == kTileM, DURF_E_UNSUPPORTED, "durf_mlp_bwd(bf16): needs 128 samples per ray (got %d)", a.N);
@@ -438,7 +502,7 @@ int mlp_tc_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rg
   P.saved = (const uint8_t*)a.saved; P.dz = (uint8_t*)a.workspace;
   P.packed_t = (const uint8_t*)a.packed + mlp_tc_packed_bytes(t);
   P.params = a.params; P.d_raw_rgb = d_raw_rgb; P.d_raw_density = d_raw_density;
-  P.ray_index = a.ray_index; P.count = a.count; P.M = a.M; P.trace = 0;
+  P.ray_index = a.ray_index; P.count = a.count; P.M = a.M; P.trace = 0; P.d_features = d_features;
   int rc = mlp_tc_dgrad_launch(st, t, P);
   if (rc != DURF_OK) return rc;
   return mlp_tc_wgrad_run(st, t, (const uint8_t*)a.saved, (const uint8_t*)a.features, (const uint8_t*)a.workspace, d_raw_rgb,

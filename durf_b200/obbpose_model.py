@@ -94,10 +94,10 @@ class MipNerfModel:
         parameters live in `variables`, as `self.param('box_centers', ...)` does after initialisation).
         When `ctx` (a dict) is given the forward keeps what the backward pass needs in it."""
         prec = L.PREC_BF16 if self.precision == 'bf16' else L.PREC_FP32
-        # Joint box-pose optimisation needs the gradient w.r.t. the object MLPs' input features, which only the fp32 kernels
-        # produce: with precision='bf16' the object MLPs then run in fp32 (few rays hit a box), the background stays bf16.
+        # Joint box-pose optimisation needs the gradient w.r.t. the object MLPs' input features.  The tensor-core backward
+        # produces it for width-128 networks (the BoxMLP default); other widths fall to the fp32 kernels for the objects.
         pose_train = ctx is not None and self.dynamics and not (self.no_pose_opt and self.no_yaw_opt)
-        obj_prec = L.PREC_FP32 if pose_train else prec
+        obj_prec = L.PREC_FP32 if (pose_train and self.box_net_width != 128) else prec
         N = self.num_samples
         origins, dirs = ops.f32(rays.origins), ops.f32(rays.directions)
         B = origins.shape[0]

@@ -248,8 +248,9 @@ def mlp_bwd(topo, features, cond, blob, saved, d_raw_rgb, d_raw_density, d_blob,
     lib = L.load()
     nbytes = int(lib.durf_mlp_workspace_bytes(C.byref(t), precision, M, N, 1))
     ws = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
-    if want_d_features and precision != L.PREC_FP32:
-        raise L.DurfError("the tensor-core backward produces no input gradient; use precision='fp32' for the box-pose gradient")
+    if want_d_features and precision != L.PREC_FP32 and t.width != 128:
+        raise L.DurfError("the tensor-core backward produces the input gradient for width-128 networks (BoxMLP) only; "
+                          "use precision='fp32'")
     dfeat = torch.empty(M * N, t.in_dim, device=dev) if want_d_features else None
     a = _mlp_args(t, precision, M, N, features, f32(cond), f32(blob), packed, ray_index, count, False, d_raw_rgb, d_raw_density,
                   saved, ws)
