@@ -183,7 +183,7 @@ def cpu_baseline(mlp, c2w, centers, ext_np):
                 sample=f"{n} random pixels of the same frame, one pass of oracle.model_forward ({dt:.1f} s), torch fp32 on {cores} threads")
 
 
-def train_bench(dev, rank, world, steps, warmup, precision):
+def train_bench(dev, rank, world, steps, warmup, precision, pose=False):
     """C3 (BASELINE.json configs[2]): one optimisation step on 16,384 rays per GPU -- dynamic scene (background + 2 object
     NeRFs), mip360 contraction, stratified + hierarchical sampling with explicit random buffers, RGB + URF LIDAR depth /
     line-of-sight (near, empty) + sky + distortion losses, backward, gradient mean over ranks (NCCL), clip, Adam.
@@ -202,7 +202,7 @@ def train_bench(dev, rank, world, steps, warmup, precision):
     mlp = S.glorot_mlp(rng_w, 60, 256, 0.0)
     box_mlps = [S.glorot_mlp(rng_w, 63, 128, 0.0) for _ in range(K)]
     tg = S.targets(rng, B)
-    pose = os.environ.get("DURF_BENCH_POSE_OPT", "0") == "1"      # C5: joint box-pose optimisation (object MLPs then run in fp32)
+    pose = pose or os.environ.get("DURF_BENCH_POSE_OPT", "0") == "1"      # C5: joint box-pose optimisation
     model = MipNerfModel(precision=precision, num_objects=K, no_pose_opt=not pose, no_yaw_opt=not pose)
     v = Variables.allocate(model, K, centers.shape[0], dev)
     v.load_mlp("MLP_0", mlp)
@@ -420,6 +420,9 @@ def main():
         del dev_rays, out_rgb, out_dist, out_acc
         torch.cuda.empty_cache()
         train = train_bench(dev, rank, world, args.train_steps, 3, args.precision)
+        pose = train_bench(dev, rank, world, args.train_steps, 3, args.precision, pose=True)     # C5: + gradients into the SE(3) box poses
+        train["pose_opt"] = dict(value=pose["value"], unit="rays/s", ms_per_step=pose["ms_per_step"],
+                                 config="C5: same step with no_pose_opt = no_yaw_opt = False, alpha = 4.5 (BARF-weighted IPE)")
 
     if rank != 0:
         if world > 1:

@@ -261,3 +261,30 @@ def test_render_camera_equals_render_image_on_host_rays():
     b = render_camera(fn, sc['c2w'], w, h, f, 0.0, 40.0, None, ext, 0, None, 10.0, chunk=256)
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def test_full_size_chunk_properties():
+    """BASELINE-size launch (one 65,536-ray render chunk, 2 x 128 samples, tensor-core path) checked through size-independent
+    properties of the path: resampled fenceposts sorted and inside [near, far]; weights >= 0 and summing to acc <= 1;
+    un-normalised distance <= far * acc; rgb inside [0, 1]; the forward pass is deterministic (bit-identical twice)."""
+    from durf_b200 import ops, synthetic as S
+    rng = np.random.default_rng(S.SEED)
+    c2w = S.random_c2w(rng)
+    model = _model(precision='bf16', dynamics=False)
+    sc = H.scene(B=8, K=1, seed=2, behind=True)
+    v = H.cuda_variables(sc, model)
+    ext = torch.from_numpy(sc['ext']).cuda()
+    rays = ops.generate_rays(c2w, S.WAYMO_W, S.WAYMO_H, S.FOCAL, 0.0, 40.0, row0=600, row1=600 + 34)     # 65,280 rays
+    run = lambda: model.apply(v, None, rays, None, ext, 0, False, False, False, 10.0)
+    a, b = run(), run()
+    for la, lb in zip(a, b):
+        for x, y in zip(la[:7], lb[:7]):
+            assert torch.equal(x, y), "forward pass is not deterministic"
+    for lvl in a:
+        rgb, dist, acc, w, t = lvl[0], lvl[1], lvl[2], lvl[3], lvl[4]
+        assert bool(torch.isfinite(rgb).all() and torch.isfinite(w).all())
+        assert bool((t[:, 1:] >= t[:, :-1]).all()) and float(t.min()) >= 0.0 and float(t.max()) <= 40.0 * (1 + 1e-6)
+        assert float(w.min()) >= 0.0
+        assert float((w.sum(-1) - acc).abs().max()) <= 1e-4 and float(acc.max()) <= 1.0 + 1e-5
+        assert bool((dist <= 40.0 * float(np.linalg.norm(rays.directions.cpu().numpy(), axis=-1).max()) * acc + 1e-3).all())
+        assert float(rgb.min()) >= 0.0 and float(rgb.max()) <= 1.0 + 1e-5
