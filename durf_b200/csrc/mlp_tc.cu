@@ -280,16 +280,42 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     uint32_t stg_buf = 0;                         // SAVE: which of this warp's two 4 KB staging pieces the next epilogue fills
     const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 128;
     long long e_acc = 0, e_ld = 0, e_math = 0, e_st = 0, e_begin = clock64(), eq = 0, e_m0 = 0, e_ld1 = 0, e_m1 = 0;
+    // Per-tile housekeeping (raw outputs of the PREVIOUS tile, view bias of this one) is deferred until after layer 0's
+    // epilogues, when the tensor core has a whole layer of MMAs queued: the tile boundary costs the issuer nothing.
+    float den_prev = 0.f, rgb_prev[3] = {0.f, 0.f, 0.f};
+    int ray_prev = -1;
+    auto flush_prev = [&]() {      // ch == 0 threads: combine the two column slices of every row, write raw outputs
+      const size_t o = (size_t)ray_prev * kTileM + row;
+      const float dv = den_prev + s_part[row] + s_hb[0];
+      const float r0 = rgb_prev[0] + s_part[128 + row] + s_hb[1];
+      const float r1 = rgb_prev[1] + s_part[256 + row] + s_hb[2];
+      const float r2 = rgb_prev[2] + s_part[384 + row] + s_hb[3];
+      if (p.accumulate) {
+        p.raw_density[o] += dv;
+        p.raw_rgb[o * 3 + 0] += r0; p.raw_rgb[o * 3 + 1] += r1; p.raw_rgb[o * 3 + 2] += r2;
+      } else {
+        p.raw_density[o] = dv;
+        p.raw_rgb[o * 3 + 0] = r0; p.raw_rgb[o * 3 + 1] = r1; p.raw_rgb[o * 3 + 2] = r2;
+      }
+    };
+    // per-ray bias of the condition layer (b + W_view^T enc(viewdir), obbpose_model.py:343-350): fetched a tile ahead
+    float vb_next = (ch == 0 && (int)blockIdx.x < num_tiles) ? p.vbias[(size_t)blockIdx.x * 128 + row] : 0.f;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int ray = p.ray_index ? p.ray_index[tile] : tile;
-      // per-ray bias of the condition layer (b + W_view^T enc(viewdir), obbpose_model.py:343-350), precomputed per tile
-      const float vb_mine = (ch == 0) ? p.vbias[(size_t)tile * 128 + row] : 0.f;    // consumed only at the last layer
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // previous tile's readers of s_vbias / s_part are done
-      if (ch == 0) s_vbias[row] = vb_mine;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float vb_mine = vb_next;
+      const int tile_next = tile + (int)gridDim.x;
+      vb_next = (ch == 0 && tile_next < num_tiles) ? p.vbias[(size_t)tile_next * 128 + row] : 0.f;
       float den = 0.f;
       float rgb[3] = {0.f, 0.f, 0.f};
       for (int g = 0; g < p.G; ++g) {
+        if (g == 1) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");   // s_part of the previous tile is complete; its s_vbias readers are done
+          if (ch == 0) {
+            if (ray_prev >= 0) flush_prev();
+            s_vbias[row] = vb_mine;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
         const LayerSched& L = p.sched[g];
         const uint32_t o_buf = t_lane + C::ACT_COL + ((g + 1) & 1) * (W / 2);
         for (int h = 0; h < L.n_halves; ++h) {
@@ -395,25 +421,17 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       if (tr && tile + (int)gridDim.x >= num_tiles)
         printf("durf mlp_tc trace: epilogue thread: total %lld cyc; waiting acc_full %lld, tmem ld %lld, math+st issue %lld (g0 %lld, ld1 wait %lld, g1 %lld), st wait %lld\n",
                clock64() - e_begin, e_acc, e_ld, e_math, e_m0, e_ld1, e_m1, e_st);
-      // combine the two column slices of every row and write the raw outputs
+      // stash this tile's head results: they are combined and written while the next tile's layer 1 runs
       if (ch == 1) {
         s_part[row] = den; s_part[128 + row] = rgb[0]; s_part[256 + row] = rgb[1]; s_part[384 + row] = rgb[2];
+      } else {
+        den_prev = den; rgb_prev[0] = rgb[0]; rgb_prev[1] = rgb[1]; rgb_prev[2] = rgb[2];
       }
+      ray_prev = ray;
+    }
+    if (ray_prev >= 0) {             // the last tile's outputs
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (ch == 0) {
-        const size_t o = (size_t)ray * kTileM + row;
-        const float dv = den + s_part[row] + s_hb[0];
-        const float r0 = rgb[0] + s_part[128 + row] + s_hb[1];
-        const float r1 = rgb[1] + s_part[256 + row] + s_hb[2];
-        const float r2 = rgb[2] + s_part[384 + row] + s_hb[3];
-        if (p.accumulate) {
-          p.raw_density[o] += dv;
-          p.raw_rgb[o * 3 + 0] += r0; p.raw_rgb[o * 3 + 1] += r1; p.raw_rgb[o * 3 + 2] += r2;
-        } else {
-          p.raw_density[o] = dv;
-          p.raw_rgb[o * 3 + 0] = r0; p.raw_rgb[o * 3 + 1] = r1; p.raw_rgb[o * 3 + 2] = r2;
-        }
-      }
+      if (ch == 0) flush_prev();
     }
   }
   if (SAVE && warp >= 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staged activations are in HBM
