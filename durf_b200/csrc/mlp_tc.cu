@@ -186,9 +186,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
           const ChunkSched ck = p.chunks[c];
           mbar_wait(bar_empty(stage), phase ^ 1);
           mbar_arrive_expect_tx(bar_full(stage), ck.nkb * kBlockBytes);
-          for (int kb = 0; kb < ck.nkb; ++kb)
-            bulk_g2s(sbase + C::OFF_RING + stage * C::STAGE_BYTES + kb * kBlockBytes,
-                     p.packed + (size_t)(ck.block0 + kb) * kBlockBytes, kBlockBytes, bar_full(stage));
+          // the chunk's K blocks are contiguous in the packed image: one copy
+          bulk_g2s(sbase + C::OFF_RING + stage * C::STAGE_BYTES, p.packed + (size_t)ck.block0 * kBlockBytes,
+                   ck.nkb * kBlockBytes, bar_full(stage));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }

@@ -160,9 +160,8 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
           for (int nh = 0; nh < S.n_halves; ++nh) {
             mbar_wait(bar_empty(stage), phase ^ 1);
             mbar_arrive_expect_tx(bar_full(stage), S.n_kb * kBlockBytes);
-            for (int kb = 0; kb < S.n_kb; ++kb)
-              bulk_g2s(sbase + C::OFF_RING + stage * C::STAGE_BYTES + kb * kBlockBytes,
-                       p.packed_t + (size_t)(S.block0 + nh * S.n_kb + kb) * kBlockBytes, kBlockBytes, bar_full(stage));
+            bulk_g2s(sbase + C::OFF_RING + stage * C::STAGE_BYTES, p.packed_t + (size_t)(S.block0 + nh * S.n_kb) * kBlockBytes,
+                     S.n_kb * kBlockBytes, bar_full(stage));
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
