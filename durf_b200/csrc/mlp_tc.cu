@@ -147,13 +147,14 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
   auto bar_empty = [&](int s) { return bar0 + 8 * (kMaxStages + s); };
   const uint32_t bar_inp_full = bar0 + 8 * (2 * kMaxStages), bar_inp_empty = bar0 + 8 * (2 * kMaxStages + 1);
   auto bar_acc_full = [&](int h) { return bar0 + 8 * (2 * kMaxStages + 2 + h); };
-  auto bar_a_ready = [&](int h) { return bar0 + 8 * (2 * kMaxStages + 4 + h); };
-  static_assert(32 + 8 * (2 * kMaxStages + 6) <= C::MISC_BYTES, "barrier area");
+  auto bar_a_ready = [&](int kb) { return bar0 + 8 * (2 * kMaxStages + 4 + kb); };   // one per 64-column K block of the next layer's A
+  static_assert(32 + 8 * (2 * kMaxStages + 8) <= C::MISC_BYTES, "barrier area");
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     mbar_init(bar_inp_full, 1); mbar_init(bar_inp_empty, 1);
-    for (int h = 0; h < 2; ++h) { mbar_init(bar_acc_full(h), 1); mbar_init(bar_a_ready(h), 256); }
+    for (int h = 0; h < 2; ++h) mbar_init(bar_acc_full(h), 1);
+    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_a_ready(kb), 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -200,7 +201,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       constexpr uint32_t idesc = umma_idesc(128, 128);
       constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);     // SBO | version | SWIZZLE_128B
       uint32_t stage = 0, phase = 0;
-      uint32_t ar_par[2] = {0, 0}, inp_par = 0;
+      uint32_t ar_par[4] = {0, 0, 0, 0}, inp_par = 0;
       int it = 0;
       const bool tr = p.trace && blockIdx.x == 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -214,8 +215,10 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
             if (tr) tq = clock64();
             mbar_wait(bar_inp_full, inp_par); inp_par ^= 1;
             if (tr) { t_inp += clock64() - tq; tq = clock64(); }
-            if (it > 0)      // accumulators of the previous tile's last layer must have been drained
-              for (int h = 0; h < halves_last; ++h) { mbar_wait(bar_a_ready(h), ar_par[h]); ar_par[h] ^= 1; }
+            if (it > 0) {    // accumulators of the previous tile's last layer must have been drained
+              mbar_wait(bar_a_ready(0), ar_par[0]); ar_par[0] ^= 1;
+              if (halves_last > 1) { mbar_wait(bar_a_ready(2), ar_par[2]); ar_par[2] ^= 1; }
+            }
             if (tr) t_ready += clock64() - tq;
           }
           if (tr) tq = clock64();
@@ -228,9 +231,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
             for (int kb = 0; kb < C::KB; ++kb) {
               if (kb < ck.nkb) {
-                if (ck.nh == 0 && (kb & 1) == 0) {   // first K block produced by half kb/2 of the previous layer's epilogue
+                if (ck.nh == 0) {   // K block kb of this layer's A operand: written by the previous layer's epilogue
                   if (tr) tq = clock64();
-                  mbar_wait(bar_a_ready(kb >> 1), ar_par[kb >> 1]); ar_par[kb >> 1] ^= 1;
+                  mbar_wait(bar_a_ready(kb), ar_par[kb]); ar_par[kb] ^= 1;
                   tc_fence_after();
                   if (tr) t_ready += clock64() - tq;
                 }
@@ -330,30 +333,40 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
           }
           tc_fence_after();
           uint32_t v[NG][32];
-          tmem_ld32_issue(t_lane + C::ACC_COL + col0, v[0]);
           if (L.kind != 3) {
-            // software pipeline over the two 32-column groups: the TMEM load of group 1 and the bias fetches run
-            // under the arithmetic of group 0 (TMEM reads are the epilogue's floor: 32 B/cycle per lane quarter)
-            const uint32_t sb = sbase + C::OFF_BIAS + (g * W + col0) * 4;
+            // software pipeline over two 32-column groups: the TMEM load of group 1 and the bias fetches run
+            // under the arithmetic of group 0 (TMEM reads are the epilogue's floor: 32 B/cycle per lane quarter).
+            // Inference: group i of every warp lies in K block 2h+i of the next layer's A operand, so the eight warps
+            // finish block 2h first and the issuer can start on it while block 2h+1 is still being packed.  Training keeps
+            // each warp on 64 adjacent columns (its 4 KB piece of the saved activation image).
+            auto gcol = [&](int i) { return SAVE ? col0 + i * 32 : h * 128 + i * 64 + ch * 32; };
+            tmem_ld32_issue(t_lane + C::ACC_COL + gcol(0), v[0]);
 #pragma unroll
             for (int i = 0; i < NG; ++i) {
+              const int cg = gcol(i);
+              const uint32_t sb = sbase + C::OFF_BIAS + (g * W + cg) * 4;
               float4 b4[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) b4[j] = lds128(sb + (i * 32 + 4 * j) * 4);
+              for (int j = 0; j < 8; ++j) b4[j] = lds128(sb + 16 * j);
               long long tq1 = 0;
               if (tr && i == 1) tq1 = clock64();
               tmem_ld_wait();
               tmem_ld_pin(v[i]);
               if (tr && i == 1) e_ld1 += clock64() - tq1;
-              if (i + 1 < NG) tmem_ld32_issue(t_lane + C::ACC_COL + col0 + (i + 1) * 32, v[i + 1]);
+              if (i + 1 < NG) tmem_ld32_issue(t_lane + C::ACC_COL + gcol(i + 1), v[i + 1]);
               if (tr && i == 0) { e_ld += clock64() - eq; eq = clock64(); }
               if (tr) tq1 = clock64();
               uint32_t pk[16];
-              const uint32_t wden_addr = sbase + C::OFF_WDEN + (col0 + i * 32) * 4;
+              const uint32_t wden_addr = sbase + C::OFF_WDEN + cg * 4;
               if (L.kind == 0) epi_pack<0>(v[i], b4, wden_addr, den, pk);
               else if (L.kind == 1) epi_pack<1>(v[i], b4, wden_addr, den, pk);
               else epi_pack<2>(v[i], b4, wden_addr, den, pk);
-              tmem_st16(o_buf + (col0 + i * 32) / 2, pk);
+              tmem_st16(o_buf + cg / 2, pk);
+              if constexpr (!SAVE) {
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(bar_a_ready(2 * h + i));   // K block 2h+i of the next layer's A operand is in TMEM
+              }
               if (tr) { if (i == 0) e_m0 += clock64() - tq1; else e_m1 += clock64() - tq1; }
               if constexpr (SAVE) {
                 // training: keep the activation (A operand of wgrad, ReLU mask of dgrad).  The warp's 32 rows x 64 columns
@@ -382,19 +395,22 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
               stg_buf ^= 1;
             }
             if (tr) { e_math += clock64() - eq; eq = clock64(); }
-            tmem_st_wait();
+            if constexpr (SAVE) {
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(bar_a_ready(2 * h));   // half h (K blocks 2h, 2h+1) of the next layer's A operand is in TMEM
+              mbar_arrive(bar_a_ready(2 * h + 1));
+            }
             if (tr) e_st += clock64() - eq;
-            tc_fence_before();
-            mbar_arrive(bar_a_ready(h));   // half h of the next layer's A operand is in TMEM
           } else {
             // condition layer: + per-ray bias, ReLU, partial rgb head over this warp's columns
 #pragma unroll
-            for (int i = 1; i < NG; ++i) tmem_ld32_issue(t_lane + C::ACC_COL + col0 + i * 32, v[i]);
+            for (int i = 0; i < NG; ++i) tmem_ld32_issue(t_lane + C::ACC_COL + col0 + i * 32, v[i]);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < NG; ++i) tmem_ld_pin(v[i]);
             tc_fence_before();
-            mbar_arrive(bar_a_ready(h));   // accumulators drained: the next tile's first layer may overwrite them
+            mbar_arrive(bar_a_ready(2 * h));   // accumulators drained: the next tile's first layer may overwrite them
             const uint32_t svb = sbase + C::OFF_VBIAS + col0 * 4, swr = sbase + C::OFF_WRGB + col0 * 4;
 #pragma unroll
             for (int i = 0; i < NG; ++i)
