@@ -154,7 +154,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     mbar_init(bar_inp_full, 1); mbar_init(bar_inp_empty, 1);
     for (int h = 0; h < 2; ++h) mbar_init(bar_acc_full(h), 1);
-    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_a_ready(kb), 256);
+    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_a_ready(kb), 8);   // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -205,7 +205,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       int it = 0;
       const bool tr = p.trace && blockIdx.x == 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      long long t_full = 0, t_ready = 0, t_inp = 0, t_begin = clock64(), tq = 0;
+      long long t_full = 0, t_ready = 0, t_inp = 0, t_begin = clock64(), tq = 0, t_kb[4] = {0, 0, 0, 0};
       const uint32_t inp_lo = ((sbase + C::OFF_INP) & 0x3FFFF) >> 4 | (1u << 16);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         for (int c = 0; c < p.n_chunks; ++c) {
@@ -235,7 +235,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
                   if (tr) tq = clock64();
                   mbar_wait(bar_a_ready(kb), ar_par[kb]); ar_par[kb] ^= 1;
                   tc_fence_after();
-                  if (tr) t_ready += clock64() - tq;
+                  if (tr) { t_ready += clock64() - tq; t_kb[kb] += clock64() - tq; }
                 }
 #pragma unroll
                 for (int k16 = 0; k16 < 4; ++k16)
@@ -252,8 +252,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if (tr && lane == 0) printf("durf mlp_tc trace: MMA thread: %d tiles, total %lld cyc; waiting weights %lld, epilogue(a_ready) %lld, features %lld\n",
-                     it, clock64() - t_begin, t_full, t_ready, t_inp);
+      if (tr && lane == 0) printf("durf mlp_tc trace: MMA thread: %d tiles, total %lld cyc; waiting weights %lld, epilogue(a_ready) %lld (K block 0: %lld, 1: %lld, 2: %lld, 3: %lld), features %lld\n",
+                     it, clock64() - t_begin, t_full, t_ready, t_kb[0], t_kb[1], t_kb[2], t_kb[3], t_inp);
     }
   } else if (warp == 2) {
     // ===== feature-tile loader: the next tile's features arrive while the layers after the skip layer run =====
@@ -273,7 +273,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     const int ch = (warp - 4) >> 2;               // which 64-column slice of a half this warp owns
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t af_par[2] = {0, 0};
+    uint32_t af_par = 0;                          // bit h: parity of acc_full(h)
     constexpr int NG = C::CPW / 32;               // 32-column groups per warp per half
     // The first epilogue thread also frees weight stages / the input tile once their MMAs have retired.  It must be a
     // thread whose progress the MMA issuer depends on: a passive observer of acc_full could fall two completions behind
@@ -319,21 +319,27 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
+        // the layer's schedule entry is fetched before the wait: nothing between the accumulator barrier and the first
+        // TMEM load may depend on a constant-bank round trip (this gap is on the layer-to-layer critical path)
         const LayerSched& L = p.sched[g];
+        const int kind = L.kind, n_halves = L.n_halves;
+        const int n_rel = (L.n_act_kb > 0 ? 1 : 0) + L.uses_inp;
+        const bool rel_inp = L.last_inp_use != 0;
         const uint32_t o_buf = t_lane + C::ACT_COL + ((g + 1) & 1) * (W / 2);
-        for (int h = 0; h < L.n_halves; ++h) {
+        for (int h = 0; h < n_halves; ++h) {
           const int col0 = h * 128 + ch * C::CPW;
           if (tr) eq = clock64();
-          mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
+          mbar_wait(bar_acc_full(h), (af_par >> h) & 1u); af_par ^= 1u << h;
           if (tr) { e_acc += clock64() - eq; eq = clock64(); }
-          if (releaser) {
-            const int n_rel = (L.n_act_kb > 0 ? 1 : 0) + L.uses_inp;
-            for (int r = 0; r < n_rel; ++r) { mbar_arrive(bar_empty(rel_stage)); if (++rel_stage == C::STAGES) rel_stage = 0; }
-            if (L.last_inp_use && h == L.n_halves - 1) mbar_arrive(bar_inp_empty);
-          }
           tc_fence_after();
+          auto release = [&]() {      // after the first TMEM load is in flight
+            if (releaser) {
+              for (int r = 0; r < n_rel; ++r) { mbar_arrive(bar_empty(rel_stage)); if (++rel_stage == C::STAGES) rel_stage = 0; }
+              if (rel_inp && h == n_halves - 1) mbar_arrive(bar_inp_empty);
+            }
+          };
           uint32_t v[NG][32];
-          if (L.kind != 3) {
+          if (kind != 3) {
             // software pipeline over two 32-column groups: the TMEM load of group 1 and the bias fetches run
             // under the arithmetic of group 0 (TMEM reads are the epilogue's floor: 32 B/cycle per lane quarter).
             // Inference: group i of every warp lies in K block 2h+i of the next layer's A operand, so the eight warps
@@ -341,6 +347,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
             // each warp on 64 adjacent columns (its 4 KB piece of the saved activation image).
             auto gcol = [&](int i) { return SAVE ? col0 + i * 32 : h * 128 + i * 64 + ch * 32; };
             tmem_ld32_issue(t_lane + C::ACC_COL + gcol(0), v[0]);
+            release();
 #pragma unroll
             for (int i = 0; i < NG; ++i) {
               const int cg = gcol(i);
@@ -358,14 +365,15 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
               if (tr) tq1 = clock64();
               uint32_t pk[16];
               const uint32_t wden_addr = sbase + C::OFF_WDEN + cg * 4;
-              if (L.kind == 0) epi_pack<0>(v[i], b4, wden_addr, den, pk);
-              else if (L.kind == 1) epi_pack<1>(v[i], b4, wden_addr, den, pk);
+              if (kind == 0) epi_pack<0>(v[i], b4, wden_addr, den, pk);
+              else if (kind == 1) epi_pack<1>(v[i], b4, wden_addr, den, pk);
               else epi_pack<2>(v[i], b4, wden_addr, den, pk);
               tmem_st16(o_buf + cg / 2, pk);
               if constexpr (!SAVE) {
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(bar_a_ready(2 * h + i));   // K block 2h+i of the next layer's A operand is in TMEM
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_a_ready(2 * h + i));   // K block 2h+i of the next layer's A operand is in TMEM
               }
               if (tr) { if (i == 0) e_m0 += clock64() - tq1; else e_m1 += clock64() - tq1; }
               if constexpr (SAVE) {
@@ -398,19 +406,24 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
             if constexpr (SAVE) {
               tmem_st_wait();
               tc_fence_before();
-              mbar_arrive(bar_a_ready(2 * h));   // half h (K blocks 2h, 2h+1) of the next layer's A operand is in TMEM
-              mbar_arrive(bar_a_ready(2 * h + 1));
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive(bar_a_ready(2 * h));   // half h (K blocks 2h, 2h+1) of the next layer's A operand is in TMEM
+                mbar_arrive(bar_a_ready(2 * h + 1));
+              }
             }
             if (tr) e_st += clock64() - eq;
           } else {
             // condition layer: + per-ray bias, ReLU, partial rgb head over this warp's columns
 #pragma unroll
             for (int i = 0; i < NG; ++i) tmem_ld32_issue(t_lane + C::ACC_COL + col0 + i * 32, v[i]);
+            release();
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < NG; ++i) tmem_ld_pin(v[i]);
             tc_fence_before();
-            mbar_arrive(bar_a_ready(2 * h));   // accumulators drained: the next tile's first layer may overwrite them
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a_ready(2 * h));   // accumulators drained: the next tile's first layer may overwrite them
             const uint32_t svb = sbase + C::OFF_VBIAS + col0 * 4, swr = sbase + C::OFF_WRGB + col0 * 4;
 #pragma unroll
             for (int i = 0; i < NG; ++i)
