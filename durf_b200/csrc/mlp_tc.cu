@@ -205,55 +205,63 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       int it = 0;
       const bool tr = p.trace && blockIdx.x == 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      long long t_full = 0, t_ready = 0, t_inp = 0, t_begin = clock64(), tq = 0, t_kb[4] = {0, 0, 0, 0};
+      long long t_start = 0, t_begin = clock64(), tq = 0;
       const uint32_t inp_lo = ((sbase + C::OFF_INP) & 0x3FFFF) >> 4 | (1u << 16);
+      // Every K block of MMAs waits - inside umma_kblock_conv, after its MMAs are queued - for the barriers of the NEXT
+      // K block, so the thread itself never sits in a wait with an empty tensor queue behind it.  Only the first weights
+      // and the per-tile start conditions are waited for up front.
+      if (blockIdx.x < num_tiles) mbar_wait(bar_full(0), 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const bool more_tiles = tile + (int)gridDim.x < num_tiles;
         for (int c = 0; c < p.n_chunks; ++c) {
           const ChunkSched ck = p.chunks[c];
           const uint32_t d_addr = tmem_u + C::ACC_COL + ck.nh * 128;
           if (c == 0) {
             if (tr) tq = clock64();
             mbar_wait(bar_inp_full, inp_par); inp_par ^= 1;
-            if (tr) { t_inp += clock64() - tq; tq = clock64(); }
             if (it > 0) {    // accumulators of the previous tile's last layer must have been drained
               mbar_wait(bar_a_ready(0), ar_par[0]); ar_par[0] ^= 1;
               if (halves_last > 1) { mbar_wait(bar_a_ready(2), ar_par[2]); ar_par[2] ^= 1; }
             }
-            if (tr) t_ready += clock64() - tq;
+            if (tr) t_start += clock64() - tq;
           }
-          if (tr) tq = clock64();
-          mbar_wait(bar_full(stage), phase);
-          if (tr) t_full += clock64() - tq;
-          tc_fence_after();
+          tc_fence_after();      // this chunk's weights (and its first K block) were waited for by the previous K block
+          // what the first K block of the next chunk needs: its weights, and K block 0 of its A operand if it opens a layer
+          const bool last_chunk = c + 1 == p.n_chunks;
+          const uint32_t next_stage = (stage + 1 == C::STAGES) ? 0 : stage + 1;
+          const uint32_t next_phase = (stage + 1 == C::STAGES) ? phase ^ 1 : phase;
+          const uint32_t need_w = (!last_chunk || more_tiles) ? 1u : 0u;
+          const uint32_t need_a0 = (!last_chunk && p.chunks[c + 1].nh == 0 && !p.chunks[c + 1].inp) ? 1u : 0u;
           const uint32_t b_lo = (((sbase + C::OFF_RING + stage * C::STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
           if (!ck.inp) {
             const uint32_t a_buf = tmem_u + C::ACT_COL + (ck.g & 1) * (W / 2);     // written by the epilogue of layer g-1
 #pragma unroll
             for (int kb = 0; kb < C::KB; ++kb) {
               if (kb < ck.nkb) {
-                if (ck.nh == 0) {   // K block kb of this layer's A operand: written by the previous layer's epilogue
-                  if (tr) tq = clock64();
-                  mbar_wait(bar_a_ready(kb), ar_par[kb]); ar_par[kb] ^= 1;
-                  tc_fence_after();
-                  if (tr) { t_ready += clock64() - tq; t_kb[kb] += clock64() - tq; }
-                }
-#pragma unroll
-                for (int k16 = 0; k16 < 4; ++k16)
-                  umma_ts_conv(d_addr, a_buf + kb * 32 + k16 * 8, b_lo + ((kb * kBlockBytes + k16 * 32) >> 4), desc_hi, idesc,
-                          (ck.first && kb == 0 && k16 == 0) ? 0u : 1u);
+                if (ck.nh == 0) { ar_par[kb] ^= 1; tc_fence_after(); }   // K block kb of the A operand (previous layer's epilogue) is there
+                const uint32_t acc0 = (ck.first && kb == 0) ? 0u : 1u;
+                if (kb + 1 < ck.nkb)
+                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo + ((kb * kBlockBytes) >> 4), desc_hi, idesc, acc0,
+                                         bar_a_ready((kb + 1) & 3), ar_par[(kb + 1) & 3], ck.nh == 0 ? 1u : 0u, bar_full(0), 0u, 0u,
+                                         bar_acc_full(ck.nh), 0u);
+                else
+                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo + ((kb * kBlockBytes) >> 4), desc_hi, idesc, acc0,
+                                         bar_a_ready(0), ar_par[0], need_a0, bar_full(next_stage), next_phase, need_w,
+                                         bar_acc_full(ck.nh), ck.last ? 1u : 0u);
               }
             }
           } else {
-#pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16)
-              umma_ss_conv(d_addr, inp_lo + ((k16 * 32) >> 4), b_lo + ((k16 * 32) >> 4), desc_hi, idesc, (ck.first && k16 == 0) ? 0u : 1u);
+            umma_kblock_conv<false>(d_addr, inp_lo, b_lo, desc_hi, idesc, ck.first ? 0u : 1u,
+                                    bar_a_ready(0), ar_par[0], need_a0, bar_full(next_stage), next_phase, need_w,
+                                    bar_acc_full(ck.nh), ck.last ? 1u : 0u);
           }
-          if (ck.last) tc_commit_conv(bar_acc_full(ck.nh));      // the epilogue releases the ring stage(s) and the input tile
+          // (the commit of a layer half's last chunk - the epilogue then releases the ring stage(s) and the input tile - is
+          // issued inside umma_kblock_conv, between the MMAs and the wait for the next chunk's barriers)
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if (tr && lane == 0) printf("durf mlp_tc trace: MMA thread: %d tiles, total %lld cyc; waiting weights %lld, epilogue(a_ready) %lld (K block 0: %lld, 1: %lld, 2: %lld, 3: %lld), features %lld\n",
-                     it, clock64() - t_begin, t_full, t_ready, t_kb[0], t_kb[1], t_kb[2], t_kb[3], t_inp);
+      if (tr && lane == 0) printf("durf mlp_tc trace: MMA thread: %d tiles, total %lld cyc; tile start (features, drained accumulators) %lld\n",
+                     it, clock64() - t_begin, t_start);
     }
   } else if (warp == 2) {
     // ===== feature-tile loader: the next tile's features arrive while the layers after the skip layer run =====

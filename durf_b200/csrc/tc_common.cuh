@@ -102,6 +102,89 @@ __device__ __forceinline__ void umma_ss_conv(uint32_t d_tmem, uint32_t a_lo, uin
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
       "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One K block (4 x K=16) of MMAs by a converged warp, bracketed by a software-pipelined wait on the barriers the NEXT
+// group of MMAs needs.  Why: an instruction of the issuing thread that returns a value through the memory pipe (mbarrier
+// test/try_wait, any load) completes only after the tcgen05.mma's issued before it have left the queue, so a wait placed
+// between two groups drains the tensor pipe (measured: 260-390 cycles for a wait on an already completed barrier).
+// Here the barriers are probed (non-blocking test_wait) BEFORE this group's MMAs and the outcome is consumed AFTER them:
+// if the data of the next group is already there - the common case - the thread never stalls with an empty queue
+// behind it; only a failed probe falls into the blocking try_wait loop.  need_x == 0 disables barrier x (pass any valid
+// barrier address).  do_commit: tcgen05.commit -> bar_commit right after the MMAs (before any blocking wait, so the
+// consumer of the accumulator is never held up by this thread's wait).  A_TMEM: A operand from tensor memory (a = TMEM address, +8 columns per K=16 step), else from a
+// shared-memory descriptor (a = descriptor lo word, +2 per step); b_lo advances by 2 (32 bytes >> 4) per step.
+template <bool A_TMEM>
+__device__ __forceinline__ void umma_kblock_conv(uint32_t d_tmem, uint32_t a, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                                 uint32_t accumulate_first, uint32_t bar_a, uint32_t par_a, uint32_t need_a,
+                                                 uint32_t bar_b, uint32_t par_b, uint32_t need_b, uint32_t bar_commit, uint32_t do_commit) {
+#define DURF_KB_WAIT(Q, BAR, PAR, L)                                             \
+      "@" Q " bra " L "_DONE;\n"                                                  \
+      L "_WAIT:\n"                                                                \
+      "mbarrier.try_wait.parity.shared::cta.b64 " Q ", [" BAR "], " PAR ";\n"     \
+      "@" Q " bra " L "_DONE;\n"                                                  \
+      "add.u32 cnt, cnt, 1;\n"                                                    \
+      "setp.lt.u32 t, cnt, 0x1000000;\n"                                          \
+      "@t bra " L "_WAIT;\n"                                                      \
+      "trap;\n"                                                                   \
+      L "_DONE:\n"
+  if constexpr (A_TMEM) {
+    asm volatile(
+        "{\n"
+        ".reg .pred e, pacc, ptrue, qa, qb, t;\n"
+        ".reg .b64 db;\n"
+        ".reg .b32 bl, al, cnt;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 qa, [%6], %7;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 qb, [%9], %10;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "setp.ne.b32 pacc, %5, 0;\n"
+        "setp.eq.u32 ptrue, %5, %5;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, pacc;\n"
+        "add.u32 bl, %2, 2;\n add.u32 al, %1, 8;\n mov.b64 db, {bl, %3};\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, ptrue;\n"
+        "add.u32 bl, %2, 4;\n add.u32 al, %1, 16;\n mov.b64 db, {bl, %3};\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, ptrue;\n"
+        "add.u32 bl, %2, 6;\n add.u32 al, %1, 24;\n mov.b64 db, {bl, %3};\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, ptrue;\n"
+        "setp.ne.u32 t, %13, 0;\n and.pred t, t, e;\n"
+        "@t tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n"
+        "setp.eq.u32 t, %8, 0;\n or.pred qa, qa, t;\n"
+        "setp.eq.u32 t, %11, 0;\n or.pred qb, qb, t;\n"
+        "mov.u32 cnt, 0;\n"
+        DURF_KB_WAIT("qa", "%6", "%7", "LA")
+        DURF_KB_WAIT("qb", "%9", "%10", "LB")
+        "}\n" ::"r"(d_tmem), "r"(a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first), "r"(bar_a), "r"(par_a), "r"(need_a),
+        "r"(bar_b), "r"(par_b), "r"(need_b), "r"(bar_commit), "r"(do_commit) : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred e, pacc, ptrue, qa, qb, t;\n"
+        ".reg .b64 da, db;\n"
+        ".reg .b32 bl, al, cnt;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 qa, [%6], %7;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 qb, [%9], %10;\n"
+        "elect.sync _|e, 0xffffffff;\n"
+        "setp.ne.b32 pacc, %5, 0;\n"
+        "setp.eq.u32 ptrue, %5, %5;\n"
+        "mov.b64 da, {%1, %3};\n mov.b64 db, {%2, %3};\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pacc;\n"
+        "add.u32 bl, %2, 2;\n add.u32 al, %1, 2;\n mov.b64 da, {al, %3};\n mov.b64 db, {bl, %3};\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, ptrue;\n"
+        "add.u32 bl, %2, 4;\n add.u32 al, %1, 4;\n mov.b64 da, {al, %3};\n mov.b64 db, {bl, %3};\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, ptrue;\n"
+        "add.u32 bl, %2, 6;\n add.u32 al, %1, 6;\n mov.b64 da, {al, %3};\n mov.b64 db, {bl, %3};\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, ptrue;\n"
+        "setp.ne.u32 t, %13, 0;\n and.pred t, t, e;\n"
+        "@t tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n"
+        "setp.eq.u32 t, %8, 0;\n or.pred qa, qa, t;\n"
+        "setp.eq.u32 t, %11, 0;\n or.pred qb, qb, t;\n"
+        "mov.u32 cnt, 0;\n"
+        DURF_KB_WAIT("qa", "%6", "%7", "LA")
+        DURF_KB_WAIT("qb", "%9", "%10", "LB")
+        "}\n" ::"r"(d_tmem), "r"(a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first), "r"(bar_a), "r"(par_a), "r"(need_a),
+        "r"(bar_b), "r"(par_b), "r"(need_b), "r"(bar_commit), "r"(do_commit) : "memory");
+  }
+#undef DURF_KB_WAIT
+}
 __device__ __forceinline__ void tc_commit_conv(uint32_t bar) {
   asm volatile(
       "{\n"
