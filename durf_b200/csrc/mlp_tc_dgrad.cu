@@ -175,39 +175,52 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
       uint32_t stage = 0, phase = 0, ar_par[2] = {0, 0}, pr_par = 0;
       int it = 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it)
+      // Barrier waits are software-pipelined as in the forward kernel (umma_kblock_conv): each K block of MMAs probes the
+      // barriers of the NEXT K block before its MMAs and consumes the outcome after them, because a wait executed between
+      // two groups of MMAs returns only once the tensor queue has drained.
+      if (blockIdx.x < num_tiles) mbar_wait(bar_full(0), 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const bool more_tiles = tile + (int)gridDim.x < num_tiles;
         for (int s = 0; s < p.n_stages; ++s) {
           const DgStage S = p.st[s];
           const uint32_t a_buf = tmem_u + C::ACT_COL + S.a_sel * (W / 2);
           const uint32_t idesc = S.ncols == 64 ? idesc64 : idesc128;
+          const bool waits_a = s > 0 && S.a_sel != 2;       // A operand written by the previous stage's epilogue, half by half
           for (int nh = 0; nh < S.n_halves; ++nh) {
             const uint32_t d_addr = tmem_u + C::ACC_COL + nh * 128;
             if (s == 0 && nh == 0) {
               if (it > 0)      // accumulators of the previous tile's last stage must have been drained
                 for (int h = 0; h < last_halves; ++h) { mbar_wait(bar_a_ready(h), ar_par[h]); ar_par[h] ^= 1; }
               mbar_wait(bar_p_ready, pr_par); pr_par ^= 1;           // dZ_cond is in TMEM
-              tc_fence_after();
             }
-            mbar_wait(bar_full(stage), phase);
-            tc_fence_after();
+            tc_fence_after();      // this chunk's weights (and its first K block) were waited for by the previous K block
+            // the chunk after this one: (s, nh+1), else (s+1, 0), else the next tile's first
+            const bool last_in_stage = nh + 1 == S.n_halves;
+            const bool last_chunk = last_in_stage && s + 1 == p.n_stages;
+            const uint32_t next_stage = (stage + 1 == C::STAGES) ? 0 : stage + 1;
+            const uint32_t next_phase = (stage + 1 == C::STAGES) ? phase ^ 1 : phase;
+            const uint32_t need_w = (!last_chunk || more_tiles) ? 1u : 0u;
+            const uint32_t need_a0 = (last_in_stage && !last_chunk && p.st[s + 1].a_sel != 2) ? 1u : 0u;
             const uint32_t b_lo = (((sbase + C::OFF_RING + stage * C::STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
 #pragma unroll
             for (int kb = 0; kb < C::KB; ++kb) {
               if (kb < S.n_kb) {
-                if (s > 0 && S.a_sel != 2 && nh == 0 && (kb & 1) == 0) {   // first K block produced by half kb/2 of the previous epilogue
-                  mbar_wait(bar_a_ready(kb >> 1), ar_par[kb >> 1]); ar_par[kb >> 1] ^= 1;
-                  tc_fence_after();
-                }
-#pragma unroll
-                for (int k16 = 0; k16 < 4; ++k16)
-                  umma_ts_conv(d_addr, a_buf + kb * 32 + k16 * 8, b_lo + ((kb * kBlockBytes + k16 * 32) >> 4), desc_hi, idesc,
-                          (S.first_part && kb == 0 && k16 == 0) ? 0u : 1u);
+                if (waits_a && nh == 0 && (kb & 1) == 0) { ar_par[kb >> 1] ^= 1; tc_fence_after(); }   // half kb/2 of the A operand is there
+                const uint32_t acc0 = (S.first_part && kb == 0) ? 0u : 1u;
+                if (kb + 1 < S.n_kb)
+                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo + ((kb * kBlockBytes) >> 4), desc_hi, idesc, acc0,
+                                         bar_a_ready(((kb + 1) >> 1) & 1), ar_par[((kb + 1) >> 1) & 1],
+                                         (waits_a && nh == 0 && ((kb + 1) & 1) == 0) ? 1u : 0u, bar_full(0), 0u, 0u, bar_acc_full(nh), 0u);
+                else
+                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo + ((kb * kBlockBytes) >> 4), desc_hi, idesc, acc0,
+                                         bar_a_ready(0), ar_par[0], need_a0, bar_full(next_stage), next_phase, need_w,
+                                         bar_acc_full(nh), S.last_part ? 1u : 0u);
               }
             }
-            if (S.last_part) tc_commit_conv(bar_acc_full(nh));
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
+      }
     }
   } else if (warp >= 4) {
     // ===== epilogue: thread = sample row; warps q and q+4 share TMEM lane quarter q and split a half's 128 columns =====
