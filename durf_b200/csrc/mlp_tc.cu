@@ -133,6 +133,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTAs of a cluster (1 or 2, chosen at launch) walk their tiles in lock step and share every weight fetch: each loads
+  // 1/nct of a ring stage and multicasts it, so the L2 -> SM weight traffic per tile drops by nct.
+  const uint32_t nct = cluster_nctarank(), crank = cluster_ctarank();
 
   float* s_bias = reinterpret_cast<float*>(smem + C::OFF_BIAS);
   float* s_wden = reinterpret_cast<float*>(smem + C::OFF_WDEN);
@@ -151,7 +154,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
   static_assert(32 + 8 * (2 * kMaxStages + 8) <= C::MISC_BYTES, "barrier area");
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), nct); }
     mbar_init(bar_inp_full, 1); mbar_init(bar_inp_empty, 1);
     for (int h = 0; h < 2; ++h) mbar_init(bar_acc_full(h), 1);
     for (int kb = 0; kb < 4; ++kb) mbar_init(bar_a_ready(kb), 8);   // one arrival per epilogue warp
@@ -173,23 +176,33 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (nct > 1) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them
   const uint32_t tmem_base = *s_tmem;
 
+  // Every CTA of a cluster runs the same number of tile iterations (ring stages are filled and released jointly); a CTA
+  // whose tile index is past the end recomputes the last tile and stores nothing.
   const int num_tiles = p.count ? min(*p.count, p.M) : p.M;
+  auto more = [&](int tile) { return tile - (int)crank < num_tiles; };
   const int halves_last = p.sched[p.G - 1].n_halves;
 
   if (warp == 0) {
     // ===== weight producer: one ring stage per (layer, N-half [, input block]) chunk =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; more(tile); tile += gridDim.x) {
         for (int c = 0; c < p.n_chunks; ++c) {
           const ChunkSched ck = p.chunks[c];
-          mbar_wait(bar_empty(stage), phase ^ 1);
-          mbar_arrive_expect_tx(bar_full(stage), ck.nkb * kBlockBytes);
-          // the chunk's K blocks are contiguous in the packed image: one copy
-          bulk_g2s(sbase + C::OFF_RING + stage * C::STAGE_BYTES, p.packed + (size_t)ck.block0 * kBlockBytes,
-                   ck.nkb * kBlockBytes, bar_full(stage));
+          const uint32_t bytes = ck.nkb * kBlockBytes;     // the chunk's K blocks are contiguous in the packed image
+          mbar_wait(bar_empty(stage), phase ^ 1);          // released by every CTA of the cluster
+          mbar_arrive_expect_tx(bar_full(stage), bytes);
+          const uint32_t dst = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
+          const uint8_t* src = p.packed + (size_t)ck.block0 * kBlockBytes;
+          if (nct == 1) {
+            bulk_g2s(dst, src, bytes, bar_full(stage));
+          } else {
+            const uint32_t part = bytes / nct;
+            bulk_g2s_multicast(dst + crank * part, src + crank * part, part, bar_full(stage), (uint16_t)((1u << nct) - 1));
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -210,9 +223,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       // Every K block of MMAs waits - inside umma_kblock_conv, after its MMAs are queued - for the barriers of the NEXT
       // K block, so the thread itself never sits in a wait with an empty tensor queue behind it.  Only the first weights
       // and the per-tile start conditions are waited for up front.
-      if (blockIdx.x < num_tiles) mbar_wait(bar_full(0), 0);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const bool more_tiles = tile + (int)gridDim.x < num_tiles;
+      if (more(blockIdx.x)) mbar_wait(bar_full(0), 0);
+      for (int tile = blockIdx.x; more(tile); tile += gridDim.x, ++it) {
+        const bool more_tiles = more(tile + (int)gridDim.x);
         for (int c = 0; c < p.n_chunks; ++c) {
           const ChunkSched ck = p.chunks[c];
           const uint32_t d_addr = tmem_u + C::ACC_COL + ck.nh * 128;
@@ -267,10 +280,10 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     // ===== feature-tile loader: the next tile's features arrive while the layers after the skip layer run =====
     if (lane == 0) {
       uint32_t par = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; more(tile); tile += gridDim.x) {
         mbar_wait(bar_inp_empty, par ^ 1);
         mbar_arrive_expect_tx(bar_inp_full, kInpBytes);
-        bulk_g2s(sbase + C::OFF_INP, p.feat + (size_t)tile * kInpBytes, kInpBytes, bar_inp_full);
+        bulk_g2s(sbase + C::OFF_INP, p.feat + (size_t)min(tile, num_tiles - 1) * kInpBytes, kInpBytes, bar_inp_full);
         par ^= 1;
       }
     }
@@ -311,8 +324,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     };
     // per-ray bias of the condition layer (b + W_view^T enc(viewdir), obbpose_model.py:343-350): fetched a tile ahead
     float vb_next = (ch == 0 && (int)blockIdx.x < num_tiles) ? p.vbias[(size_t)blockIdx.x * 128 + row] : 0.f;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int ray = p.ray_index ? p.ray_index[tile] : tile;
+    for (int tile = blockIdx.x; more(tile); tile += gridDim.x) {
+      const bool valid = tile < num_tiles;
+      const int ray = !valid ? -1 : (p.ray_index ? p.ray_index[tile] : tile);
       const float vb_mine = vb_next;
       const int tile_next = tile + (int)gridDim.x;
       vb_next = (ch == 0 && tile_next < num_tiles) ? p.vbias[(size_t)tile_next * 128 + row] : 0.f;
@@ -342,7 +356,11 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
           tc_fence_after();
           auto release = [&]() {      // after the first TMEM load is in flight
             if (releaser) {
-              for (int r = 0; r < n_rel; ++r) { mbar_arrive(bar_empty(rel_stage)); if (++rel_stage == C::STAGES) rel_stage = 0; }
+              for (int r = 0; r < n_rel; ++r) {
+                mbar_arrive(bar_empty(rel_stage));
+                if (nct > 1) mbar_arrive_cluster(bar_empty(rel_stage), crank ^ 1);   // the peer's next fill also lands here
+                if (++rel_stage == C::STAGES) rel_stage = 0;
+              }
               if (rel_inp && h == n_halves - 1) mbar_arrive(bar_inp_empty);
             }
           };
@@ -404,8 +422,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               if (lane == 0) {
                 uint8_t* gdst = p.saved + ((size_t)tile * p.saved_blocks_per_tile + g * C::KB + (col0 >> 6)) * kBlockBytes + q * 4096;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(gdst),
-                             "r"(sbase + C::OFF_STG + ((stg_buf * 8 + (warp - 4)) << 12)) : "memory");
+                if (valid)
+                  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(gdst),
+                               "r"(sbase + C::OFF_STG + ((stg_buf * 8 + (warp - 4)) << 12)) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               }
               stg_buf ^= 1;
@@ -445,7 +464,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
                 rgb[0] = fmaf(a0, w0.x, rgb[0]); rgb[0] = fmaf(a1, w0.y, rgb[0]); rgb[0] = fmaf(a2, w0.z, rgb[0]); rgb[0] = fmaf(a3, w0.w, rgb[0]);
                 rgb[1] = fmaf(a0, w1.x, rgb[1]); rgb[1] = fmaf(a1, w1.y, rgb[1]); rgb[1] = fmaf(a2, w1.z, rgb[1]); rgb[1] = fmaf(a3, w1.w, rgb[1]);
                 rgb[2] = fmaf(a0, w2.x, rgb[2]); rgb[2] = fmaf(a1, w2.y, rgb[2]); rgb[2] = fmaf(a2, w2.z, rgb[2]); rgb[2] = fmaf(a3, w2.w, rgb[2]);
-                if (SAVE) {
+                if (SAVE && valid) {
                   const int cc = col0 + c;
                   uint8_t* blk = p.saved + ((size_t)tile * p.saved_blocks_per_tile + g * C::KB + (cc >> 6)) * kBlockBytes;
                   *reinterpret_cast<uint2*>(blk + sw128_offset(row, (cc & 63) >> 3) + (cc & 7) * 2) =
@@ -455,7 +474,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
           }
         }
       }
-      if (tr && tile + (int)gridDim.x >= num_tiles)
+      if (tr && !more(tile + (int)gridDim.x))
         printf("durf mlp_tc trace: epilogue thread: total %lld cyc; waiting acc_full %lld, tmem ld %lld, math+st issue %lld (g0 %lld, ld1 wait %lld, g1 %lld), st wait %lld\n",
                clock64() - e_begin, e_acc, e_ld, e_math, e_m0, e_ld1, e_m1, e_st);
       // stash this tile's head results: they are combined and written while the next tile's layer 1 runs
@@ -474,6 +493,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
   if (SAVE && warp >= 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staged activations are in HBM
   tc_fence_before();
   __syncthreads();
+  if (nct > 1) cluster_sync_all();      // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
@@ -657,11 +677,23 @@ int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = a.M < sms ? a.M : sms;
+  // CTA pairs (one cluster per TPC) share each weight fetch by multicast; DURF_TC_CLUSTER=1 launches unpaired CTAs.
+  static const int cluster_env = getenv("DURF_TC_CLUSTER") ? atoi(getenv("DURF_TC_CLUSTER")) : 2;
+  const int nct = (cluster_env == 1 || sms < 2) ? 1 : 2;
+  const int grid_cap = sms / nct * nct;
+  const int grid_want = (a.M + nct - 1) / nct * nct;
+  const int grid = grid_want < grid_cap ? grid_want : grid_cap;
   cudaError_t e = cudaSuccess;
   auto launch = [&](auto kernel, int smem) {
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) kernel<<<grid, 384, smem, st>>>(P);
+    if (e != cudaSuccess) return;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nct; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kernel, P);
   };
   if (t.width == 256) {
     if (P.saved) launch(mlp_tc_fwd_kernel<256, true>, TcCfg<256, true>::SMEM_BYTES);
@@ -670,7 +702,7 @@ int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a) {
     if (P.saved) launch(mlp_tc_fwd_kernel<128, true>, TcCfg<128, true>::SMEM_BYTES);
     else launch(mlp_tc_fwd_kernel<128, false>, TcCfg<128, false>::SMEM_BYTES);
   }
-  DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_fwd(bf16): smem attribute: %s", cudaGetErrorString(e));
+  DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_fwd(bf16): launch: %s", cudaGetErrorString(e));
   DURF_CHECK_LAUNCH("durf_mlp_fwd(bf16)");
   return DURF_OK;
 }
