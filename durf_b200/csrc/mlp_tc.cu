@@ -58,6 +58,7 @@ struct TcParams {
   const int32_t* count;
   uint8_t* saved;            // [opt] training: every layer's bf16 activations as tile images (see mlp_tc_saved_bytes)
   int saved_blocks_per_tile;
+  uint32_t* masks;           // [opt] training: 1-bit ReLU masks of the trunk layers, [tile][layer][32-column group][row] words
   int M;
   int accumulate;
   float* raw_rgb;
@@ -403,7 +404,16 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
               }
               if (tr) { if (i == 0) e_m0 += clock64() - tq1; else e_m1 += clock64() - tq1; }
               if constexpr (SAVE) {
-                // training: keep the activation (A operand of wgrad, ReLU mask of dgrad).  The warp's 32 rows x 64 columns
+                // training: the ReLU mask dgrad needs, 1 bit per element (word k of the group holds elements 2k, 2k+1 in its
+                // halves; a non-negative bf16 half h is non-zero iff bit 15 of h + 0x7FFF is set): element 2k -> bit 15-k,
+                // element 2k+1 -> bit 31-k.  dgrad reads 4 bytes per thread and group instead of a 64-byte activation row.
+                if (kind != 2) {
+                  uint32_t mw = 0;
+#pragma unroll
+                  for (int k = 0; k < 16; ++k) mw |= ((pk[k] + 0x7FFF7FFFu) >> k) & (0x80008000u >> k);
+                  if (valid) p.masks[(((size_t)tile * p.depth + g) * (W / 32) + (cg >> 5)) * 128 + row] = mw;
+                }
+                // ... and the activation itself (A operand of wgrad).  The warp's 32 rows x 64 columns
                 // are a contiguous 4 KB piece of the global block image: stage it in shared memory in image order ...
                 if (i == 0) {
                   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the piece filled two epilogues ago was read
@@ -661,6 +671,7 @@ int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a) {
   P.vbias = (const float*)a.workspace;
   P.saved = (uint8_t*)a.saved;
   P.saved_blocks_per_tile = mlp_tc_saved_blocks(t);
+  P.masks = P.saved ? reinterpret_cast<uint32_t*>(P.saved + (size_t)a.M * P.saved_blocks_per_tile * kBlockBytes) : nullptr;
   {
     MlpLayout L(t);
     const int grid_b = a.M < 148 * 8 ? a.M : 148 * 8;

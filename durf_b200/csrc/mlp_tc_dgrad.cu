@@ -37,6 +37,8 @@ struct DgStage {
 
 struct DgParams {
   const uint8_t* saved;      // forward activations (tile records of saved_blocks blocks)
+  const uint32_t* masks;     // 1-bit ReLU masks written by the forward: [tile][trunk layer][32-column group][row]
+  int depth;
   uint8_t* dz;               // output: dz tile records (same record shape)
   const uint8_t* packed_t;   // transposed weight image
   const float* params;       // fp32 blob (density / rgb head weights)
@@ -64,8 +66,7 @@ struct DgCfg {
   static constexpr int ACT_COL = W;
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_OUT = OFF_RING + STAGES * STAGE_BYTES;     // [8 epilogue warps][4 KB] dZ pieces staged for bulk stores
-  static constexpr int OFF_MSK = OFF_OUT + 8 * 4096;                  // [8 epilogue warps][4 KB] activation pieces (ReLU masks), bulk-loaded
-  static constexpr int OFF_WDEN = OFF_MSK + 8 * 4096;                 // fp32 [W]
+  static constexpr int OFF_WDEN = OFF_OUT + 8 * 4096;                 // fp32 [W]
   static constexpr int OFF_WRGB = OFF_WDEN + W * 4;                   // fp32 [128][4] (rgb head kernel rows, padded)
   static constexpr int OFF_MISC = OFF_WRGB + 128 * 4 * 4;
   static constexpr int MISC_BYTES = 512;
@@ -76,7 +77,7 @@ struct DgCfg {
 // Masking / packing of one 32-column group, specialised per stage kind (0: linear, 1: + density term and mask, 2: mask)
 // so the unrolled body is branch-free.  Writes the group's 64 bytes of the dZ tile image row and returns the packed words.
 template <int KIND>
-__device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], const uint4 (&m4)[4], float gden, uint32_t wden_addr,
+__device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], uint32_t mw, float gden, uint32_t wden_addr,
                                         uint32_t stage_row, uint32_t r7, int chunk0, uint32_t (&pk)[16]);
 
 // keep a packed bf16 pair where the matching activation halfwords are non-zero (ReLU outputs are +0 or positive)
@@ -85,12 +86,19 @@ __device__ __forceinline__ uint32_t mask_pair(uint32_t packed, uint32_t act) {
   return packed & m;
 }
 
+// keep a packed bf16 pair (word k of a 32-column group) where the forward's mask word has the pair's bits set: element 2k
+// is bit 15-k, element 2k+1 bit 31-k; after the shift they are the sign bits of bytes 1 and 3, which PRMT replicates.
+__device__ __forceinline__ uint32_t mask_pair_bits(uint32_t packed, uint32_t mw, int k) {
+  uint32_t m;      // prmt default mode: selector nibble 8+b = byte b's sign bit replicated over the output byte
+  asm("prmt.b32 %0, %1, %2, 0xBB99;" : "=r"(m) : "r"(mw << k), "r"(0u));
+  return packed & m;
+}
+
 template <int KIND>
-__device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], const uint4 (&m4)[4], float gden, uint32_t wden_addr,
+__device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], uint32_t mw, float gden, uint32_t wden_addr,
                                         uint32_t stage_row, uint32_t r7, int chunk0, uint32_t (&pk)[16]) {
 #pragma unroll
   for (int c8 = 0; c8 < 4; ++c8) {
-    const uint32_t aw[4] = {m4[c8].x, m4[c8].y, m4[c8].z, m4[c8].w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float v0 = __uint_as_float(v[c8 * 8 + 2 * e]), v1 = __uint_as_float(v[c8 * 8 + 2 * e + 1]);
@@ -99,7 +107,7 @@ __device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], const uint4 (&m
         v0 = fmaf(gden, wd.x, v0); v1 = fmaf(gden, wd.y, v1);
       }
       uint32_t pr = cvt_bf16x2(v0, v1);
-      if (KIND != 0) pr = mask_pair(pr, aw[e]);
+      if (KIND != 0) pr = mask_pair_bits(pr, mw, c8 * 4 + e);
       pk[c8 * 4 + e] = pr;
     }
   }
@@ -127,14 +135,12 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
   auto bar_acc_full = [&](int h) { return bar0 + 8 * (16 + h); };
   auto bar_a_ready = [&](int h) { return bar0 + 8 * (18 + h); };
   const uint32_t bar_p_ready = bar0 + 8 * 20;
-  auto bar_mask = [&](int w) { return bar0 + 8 * (21 + w); };      // one per epilogue warp: its mask piece has landed
-  static_assert(16 + 8 * 29 <= C::MISC_BYTES, "barrier area");
+  static_assert(16 + 8 * 21 <= C::MISC_BYTES, "barrier area");
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int h = 0; h < 2; ++h) { mbar_init(bar_acc_full(h), 1); mbar_init(bar_a_ready(h), 256); }
     mbar_init(bar_p_ready, 256);
-    for (int w = 0; w < 8; ++w) mbar_init(bar_mask(w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -227,7 +233,8 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
     const int q = warp & 3, ch = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t af_par[2] = {0, 0}, msk_par = 0;
+    uint32_t af_par[2] = {0, 0};
+    uint32_t mw_next[2] = {0, 0};                 // mask words of the next masked epilogue, fetched one epilogue ahead
     const bool releaser = threadIdx.x == 128;     // an active participant frees the ring stages (see mlp_tc.cu)
     uint32_t rel_stage = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -265,23 +272,23 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
         mbar_arrive(bar_p_ready);
       }
       const float gden = p.d_raw_density[(size_t)ray * kTileM + row];
-      const uint32_t my_out = sbase + C::OFF_OUT + ((warp - 4) << 12), my_msk = sbase + C::OFF_MSK + ((warp - 4) << 12);
+      const uint32_t my_out = sbase + C::OFF_OUT + ((warp - 4) << 12);
       const uint32_t row_off = (lane >> 3) * 1024 + (lane & 7) * 128, r7 = lane & 7;
-      // the warp's 32 rows x 64 columns of a block image are a contiguous 4 KB piece: masks arrive by one bulk load per
-      // epilogue (issued one epilogue ahead), dZ leaves by one bulk store, so HBM traffic never blocks the epilogue
-      auto issue_mask = [&](int s2, int h2) {
-        if (lane == 0) {
-          const uint8_t* src = sv + (size_t)(p.st[s2].mask_slot + 2 * h2 + ch) * kBlockBytes + q * 4096;
-          mbar_arrive_expect_tx(bar_mask(warp - 4), 4096);
-          bulk_g2s(my_msk, src, 4096, bar_mask(warp - 4));
-        }
+      // the warp's 32 rows x 64 columns of a block image are a contiguous 4 KB piece: dZ leaves by one bulk store per epilogue;
+      // the ReLU masks are the forward's 1-bit words (one 4-byte load per thread and 32-column group, issued one epilogue
+      // ahead), so HBM traffic never blocks the epilogue
+      auto fetch_mask = [&](int s2, int h2) {
+        const int g2 = p.st[s2].mask_slot / C::KB;       // trunk layer whose activation gates this stage's output
+        const uint32_t* src = p.masks + (((size_t)tile * p.depth + g2) * (W / 32) + ((h2 * 128 + ch * 64) >> 5)) * 128 + row;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(mw_next[i]) : "l"(src + i * 128));
       };
       for (int s = 0; s < p.n_stages; ++s) {
         const DgStage S = p.st[s];
         if (!S.last_part) continue;                    // entries that only accumulate have no epilogue
         const uint32_t o_buf = t_lane + C::ACT_COL + (S.o_sel < 0 ? 0 : S.o_sel) * (W / 2);
         const bool feeds_next = S.o_sel >= 0;
-        const bool masked = S.kind == 1 || S.kind == 2;
         for (int h = 0; h < S.n_halves; ++h) {
           const int col0 = h * 128 + ch * 64;
           mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
@@ -304,28 +311,18 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
           }
           uint32_t v[32];
           tmem_ld32_issue(t_lane + C::ACC_COL + col0, v);
-          if (masked) { mbar_wait(bar_mask(warp - 4), msk_par); msk_par ^= 1; }
+          const uint32_t mw[2] = {mw_next[0], mw_next[1]};
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // previous dZ piece was read out
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            uint4 m4[4];
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              if (masked) {
-                const float4 f = lds128_volatile(my_msk + row_off + (((uint32_t)(i * 4 + c8) ^ r7) << 4));
-                m4[c8] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
-              } else {
-                m4[c8] = make_uint4(~0u, ~0u, ~0u, ~0u);
-              }
-            }
             tmem_ld_wait();
             tmem_ld_pin(v);
             uint32_t pk[16];
             const uint32_t wden_addr = sbase + C::OFF_WDEN + (col0 + i * 32) * 4;
-            if (S.kind == 0) dg_pack<0>(v, m4, gden, wden_addr, my_out + row_off, r7, i * 4, pk);
-            else if (S.kind == 1) dg_pack<1>(v, m4, gden, wden_addr, my_out + row_off, r7, i * 4, pk);
-            else dg_pack<2>(v, m4, gden, wden_addr, my_out + row_off, r7, i * 4, pk);
+            if (S.kind == 0) dg_pack<0>(v, mw[i], gden, wden_addr, my_out + row_off, r7, i * 4, pk);
+            else if (S.kind == 1) dg_pack<1>(v, mw[i], gden, wden_addr, my_out + row_off, r7, i * 4, pk);
+            else dg_pack<2>(v, mw[i], gden, wden_addr, my_out + row_off, r7, i * 4, pk);
             if (i == 0) tmem_ld32_issue(t_lane + C::ACC_COL + col0 + 32, v);
             if (feeds_next) tmem_st16(o_buf + (col0 + i * 32) / 2, pk);
             if (W == 128 && S.to_skip) tmem_st16(t_lane + C::ACT_COL + 2 * (W / 2) + (col0 + i * 32) / 2, pk);
@@ -343,7 +340,7 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
           }
           int h2 = h + 1, s2 = s;
           if (h2 >= S.n_halves) { h2 = 0; ++s2; while (s2 < p.n_stages && !p.st[s2].last_part) ++s2; }    // next entry with an epilogue
-          if (s2 < p.n_stages && (p.st[s2].kind == 1 || p.st[s2].kind == 2)) issue_mask(s2, h2);
+          if (s2 < p.n_stages && (p.st[s2].kind == 1 || p.st[s2].kind == 2)) fetch_mask(s2, h2);
         }
       }
     }
@@ -512,6 +509,8 @@ int mlp_tc_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rg
                a.workspace_bytes, need);
   DgParams P{};
   P.saved = (const uint8_t*)a.saved; P.dz = (uint8_t*)a.workspace;
+  P.masks = reinterpret_cast<const uint32_t*>(P.saved + (size_t)a.M * mlp_tc_saved_blocks(t) * kBlockBytes);
+  P.depth = t.depth;
   P.packed_t = (const uint8_t*)a.packed + mlp_tc_packed_bytes(t);
   P.params = a.params; P.d_raw_rgb = d_raw_rgb; P.d_raw_density = d_raw_density;
   P.ray_index = a.ray_index; P.count = a.count; P.M = a.M; P.trace = 0; P.d_features = d_features;

@@ -305,6 +305,31 @@ def test_mlp_tensor_core_forward(topo, M):
     assert rel(den, want_den[..., 0]) <= 2e-2, f"raw_density rel Frobenius {rel(den, want_den[..., 0]):.3e}"
 
 
+def test_mlp_tensor_core_forward_edge_counts():
+    """CTA pairs walk the tiles in lock step: a lone tile (the pair's second CTA has nothing to store), a device-side
+    count below M, and count == 0 (nothing may be written) must all behave; tiles are independent of their batch."""
+    ops = _ops()
+    from durf_b200 import _lib
+    topo, N, M = (60, 256, 8, 4, 27, 128), 128, 7
+    layers, x, cond = _mlp_inputs(topo, M, N, 77)
+    blob = _blob(topo, layers)
+    packed = ops.mlp_pack(topo, blob)
+    tiles = _tile_images(x, M, topo[0]).cuda()
+    rgb_all, den_all, _ = ops.mlp_fwd(topo, tiles, cond.cuda(), blob, M=M, N=N, precision=_lib.PREC_BF16, packed=packed)
+    rgb_1, den_1, _ = ops.mlp_fwd(topo, tiles[:1].contiguous(), cond[:1].cuda(), blob, M=1, N=N, precision=_lib.PREC_BF16, packed=packed)
+    assert torch.equal(rgb_1[0], rgb_all[0]) and torch.equal(den_1[0], den_all[0])
+    for cnt in (0, 3):
+        count = torch.tensor([cnt], dtype=torch.int32, device="cuda")
+        idx = torch.arange(M, dtype=torch.int32, device="cuda")
+        rgb = torch.full((M, N, 3), 7.0, device="cuda")
+        den = torch.full((M, N), 7.0, device="cuda")
+        ops.mlp_fwd(topo, tiles, cond.cuda(), blob, M=M, N=N, precision=_lib.PREC_BF16, packed=packed, ray_index=idx, count=count,
+                    raw_rgb=rgb, raw_density=den, num_rays_out=M)
+        torch.cuda.synchronize()
+        assert torch.equal(rgb[:cnt], rgb_all[:cnt]) and torch.equal(den[:cnt], den_all[:cnt])
+        assert bool((rgb[cnt:] == 7.0).all()) and bool((den[cnt:] == 7.0).all())
+
+
 def _tile_images(x, M, F):
     """[M,128,F] float features -> bf16 128x64 SWIZZLE_128B tile images (what the ray-march kernel writes)."""
     xb = torch.zeros(M * 128, 64)
