@@ -103,9 +103,13 @@ struct TcCfg {
   static constexpr int NHALF = W / 128;                   // N-halves per trunk layer (every tcgen05.mma is M=128, N=128)
   static constexpr int KB = W / 64;                       // 64-wide K blocks of an activation row
   static constexpr int CPW = 64;                          // columns one epilogue warp owns inside a half
-  static constexpr int STAGE_BYTES = KB * kBlockBytes;    // one ring stage holds the weights of one (layer, N-half)
-  // training (SAVE): one ring stage less, 64 KB of per-warp staging for the asynchronous bulk stores of the activations
-  static constexpr int STAGES = SAVE ? ((W == 256) ? 2 : 4) : ((W == 256) ? 3 : 6);
+  // Weight ring.  Inference: one stage per (layer, N-half) chunk (64 KB at W = 256, three of them).  Training (SAVE) gives
+  // 64 KB to the per-warp staging of the activation stores, which leaves 128 KB: two whole chunks would mean a chunk's
+  // weights can only be requested when the chunk before it has completed (measured: -17 % MMA rate), so the ring is cut into
+  // four 32 KB stages of two K blocks, each released by the MMA issuer's commit as soon as its own MMAs are done.
+  static constexpr int SKB = (SAVE && W == 256) ? 2 : KB; // K blocks per ring stage
+  static constexpr int STAGE_BYTES = SKB * kBlockBytes;
+  static constexpr int STAGES = SAVE ? 4 : ((W == 256) ? 3 : 6);
   static constexpr int TMEM_COLS = 2 * W;                 // W accumulator columns + 2 x W/2 activation columns
   static constexpr int ACC_COL = 0;
   static constexpr int ACT_COL = W;                       // buffer b at ACT_COL + b * W/2 (bf16 pairs)
@@ -193,18 +197,20 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       for (int tile = blockIdx.x; more(tile); tile += gridDim.x) {
         for (int c = 0; c < p.n_chunks; ++c) {
           const ChunkSched ck = p.chunks[c];
-          const uint32_t bytes = ck.nkb * kBlockBytes;     // the chunk's K blocks are contiguous in the packed image
-          mbar_wait(bar_empty(stage), phase ^ 1);          // released by every CTA of the cluster
-          mbar_arrive_expect_tx(bar_full(stage), bytes);
-          const uint32_t dst = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
-          const uint8_t* src = p.packed + (size_t)ck.block0 * kBlockBytes;
-          if (nct == 1) {
-            bulk_g2s(dst, src, bytes, bar_full(stage));
-          } else {
-            const uint32_t part = bytes / nct;
-            bulk_g2s_multicast(dst + crank * part, src + crank * part, part, bar_full(stage), (uint16_t)((1u << nct) - 1));
+          for (int kb0 = 0; kb0 < ck.nkb; kb0 += C::SKB) {   // the chunk's K blocks are contiguous in the packed image
+            const uint32_t bytes = (uint32_t)min(C::SKB, ck.nkb - kb0) * kBlockBytes;
+            mbar_wait(bar_empty(stage), phase ^ 1);          // released by the MMA issuer of every CTA of the cluster
+            mbar_arrive_expect_tx(bar_full(stage), bytes);
+            const uint32_t dst = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
+            const uint8_t* src = p.packed + (size_t)(ck.block0 + kb0) * kBlockBytes;
+            if (nct == 1) {
+              bulk_g2s(dst, src, bytes, bar_full(stage));
+            } else {
+              const uint32_t part = bytes / nct;
+              bulk_g2s_multicast(dst + crank * part, src + crank * part, part, bar_full(stage), (uint16_t)((1u << nct) - 1));
+            }
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -242,11 +248,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
           tc_fence_after();      // this chunk's weights (and its first K block) were waited for by the previous K block
           // what the first K block of the next chunk needs: its weights, and K block 0 of its A operand if it opens a layer
           const bool last_chunk = c + 1 == p.n_chunks;
-          const uint32_t next_stage = (stage + 1 == C::STAGES) ? 0 : stage + 1;
-          const uint32_t next_phase = (stage + 1 == C::STAGES) ? phase ^ 1 : phase;
           const uint32_t need_w = (!last_chunk || more_tiles) ? 1u : 0u;
           const uint32_t need_a0 = (!last_chunk && p.chunks[c + 1].nh == 0 && !p.chunks[c + 1].inp) ? 1u : 0u;
-          const uint32_t b_lo = (((sbase + C::OFF_RING + stage * C::STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+          const uint32_t rel_mask = nct > 1 ? (1u << nct) - 1 : 0u;
           if (!ck.inp) {
             const uint32_t a_buf = tmem_u + C::ACT_COL + (ck.g & 1) * (W / 2);     // written by the epilogue of layer g-1
 #pragma unroll
@@ -254,24 +258,34 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
               if (kb < ck.nkb) {
                 if (ck.nh == 0) { ar_par[kb] ^= 1; tc_fence_after(); }   // K block kb of the A operand (previous layer's epilogue) is there
                 const uint32_t acc0 = (ck.first && kb == 0) ? 0u : 1u;
-                if (kb + 1 < ck.nkb)
-                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo + ((kb * kBlockBytes) >> 4), desc_hi, idesc, acc0,
-                                         bar_a_ready((kb + 1) & 3), ar_par[(kb + 1) & 3], ck.nh == 0 ? 1u : 0u, bar_full(0), 0u, 0u,
-                                         bar_acc_full(ck.nh), 0u);
+                const uint32_t b_lo = (((sbase + C::OFF_RING + stage * C::STAGE_BYTES + (kb % C::SKB) * kBlockBytes) & 0x3FFFF) >> 4) | (1u << 16);
+                const bool chunk_end = kb + 1 == ck.nkb;
+                const bool stage_end = chunk_end || (kb % C::SKB) == C::SKB - 1;      // last K block read from this ring stage
+                const uint32_t next_stage = (stage + 1 == C::STAGES) ? 0 : stage + 1;
+                const uint32_t next_phase = (stage + 1 == C::STAGES) ? phase ^ 1 : phase;
+                if (!chunk_end)
+                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo, desc_hi, idesc, acc0,
+                                         bar_a_ready((kb + 1) & 3), ar_par[(kb + 1) & 3], ck.nh == 0 ? 1u : 0u,
+                                         bar_full(next_stage), next_phase, stage_end ? 1u : 0u, bar_acc_full(ck.nh), 0u,
+                                         bar_empty(stage), stage_end ? 1u : 0u, rel_mask);
                 else
-                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo + ((kb * kBlockBytes) >> 4), desc_hi, idesc, acc0,
+                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo, desc_hi, idesc, acc0,
                                          bar_a_ready(0), ar_par[0], need_a0, bar_full(next_stage), next_phase, need_w,
-                                         bar_acc_full(ck.nh), ck.last ? 1u : 0u);
+                                         bar_acc_full(ck.nh), ck.last ? 1u : 0u, bar_empty(stage), 1u, rel_mask);
+                if (stage_end) { stage = next_stage; phase = next_phase; }
               }
             }
           } else {
+            const uint32_t b_lo = (((sbase + C::OFF_RING + stage * C::STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
+            const uint32_t next_stage = (stage + 1 == C::STAGES) ? 0 : stage + 1;
+            const uint32_t next_phase = (stage + 1 == C::STAGES) ? phase ^ 1 : phase;
             umma_kblock_conv<false>(d_addr, inp_lo, b_lo, desc_hi, idesc, ck.first ? 0u : 1u,
                                     bar_a_ready(0), ar_par[0], need_a0, bar_full(next_stage), next_phase, need_w,
-                                    bar_acc_full(ck.nh), ck.last ? 1u : 0u);
+                                    bar_acc_full(ck.nh), ck.last ? 1u : 0u, bar_empty(stage), 1u, rel_mask);
+            stage = next_stage; phase = next_phase;
           }
-          // (the commit of a layer half's last chunk - the epilogue then releases the ring stage(s) and the input tile - is
-          // issued inside umma_kblock_conv, between the MMAs and the wait for the next chunk's barriers)
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          // (the commits - ring stage release, and the accumulator barrier of a layer half's last chunk - are issued inside
+          // umma_kblock_conv, between the MMAs and the wait for the next K block's barriers)
         }
       }
       if (tr && lane == 0) printf("durf mlp_tc trace: MMA thread: %d tiles, total %lld cyc; tile start (features, drained accumulators) %lld\n",
@@ -297,11 +311,10 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t af_par = 0;                          // bit h: parity of acc_full(h)
     constexpr int NG = C::CPW / 32;               // 32-column groups per warp per half
-    // The first epilogue thread also frees weight stages / the input tile once their MMAs have retired.  It must be a
-    // thread whose progress the MMA issuer depends on: a passive observer of acc_full could fall two completions behind
-    // (the ring lets the issuer run three chunks ahead) and miss a phase.
+    // The first epilogue thread frees the input tile once the MMAs of the last layer reading it have retired.  (It must be a
+    // thread whose progress the MMA issuer depends on: a passive observer of acc_full could fall two completions behind and
+    // miss a phase.)  Weight ring stages are released by the MMA issuer's own commits.
     const bool releaser = threadIdx.x == 128;
-    uint32_t rel_stage = 0;
     uint32_t stg_buf = 0;                         // SAVE: which of this warp's two 4 KB staging pieces the next epilogue fills
     const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 128;
     long long e_acc = 0, e_ld = 0, e_math = 0, e_st = 0, e_begin = clock64(), eq = 0, e_m0 = 0, e_ld1 = 0, e_m1 = 0;
@@ -346,7 +359,6 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
         // TMEM load may depend on a constant-bank round trip (this gap is on the layer-to-layer critical path)
         const LayerSched& L = p.sched[g];
         const int kind = L.kind, n_halves = L.n_halves;
-        const int n_rel = (L.n_act_kb > 0 ? 1 : 0) + L.uses_inp;
         const bool rel_inp = L.last_inp_use != 0;
         const uint32_t o_buf = t_lane + C::ACT_COL + ((g + 1) & 1) * (W / 2);
         for (int h = 0; h < n_halves; ++h) {
@@ -355,15 +367,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
           mbar_wait(bar_acc_full(h), (af_par >> h) & 1u); af_par ^= 1u << h;
           if (tr) { e_acc += clock64() - eq; eq = clock64(); }
           tc_fence_after();
-          auto release = [&]() {      // after the first TMEM load is in flight
-            if (releaser) {
-              for (int r = 0; r < n_rel; ++r) {
-                mbar_arrive(bar_empty(rel_stage));
-                if (nct > 1) mbar_arrive_cluster(bar_empty(rel_stage), crank ^ 1);   // the peer's next fill also lands here
-                if (++rel_stage == C::STAGES) rel_stage = 0;
-              }
-              if (rel_inp && h == n_halves - 1) mbar_arrive(bar_inp_empty);
-            }
+          auto release = [&]() {      // the input tile is free once the last layer reading it has completed
+            if (releaser && rel_inp && h == n_halves - 1) mbar_arrive(bar_inp_empty);
           };
           uint32_t v[NG][32];
           if (kind != 3) {

@@ -59,8 +59,11 @@ struct DgParams {
 template <int W>
 struct DgCfg {
   static constexpr int KB = W / 64;
-  static constexpr int STAGE_BYTES = KB * kBlockBytes;
-  static constexpr int STAGES = (W == 256) ? 2 : 4;
+  // weight ring: 32 KB stages of two K blocks, released by the MMA issuer's commit as soon as their own MMAs are done
+  // (with whole 64 KB chunks only two fit at W = 256 and the next chunk's weights could not be requested early enough)
+  static constexpr int SKB = 2;
+  static constexpr int STAGE_BYTES = SKB * kBlockBytes;
+  static constexpr int STAGES = (W == 256) ? 5 : 4;
   static constexpr int TMEM_COLS = (W == 128) ? 512 : 2 * W;   // W = 128 also keeps the skip layer's dZ (64 columns at ACT_COL + W)
   static constexpr int ACC_COL = 0;
   static constexpr int ACT_COL = W;
@@ -163,13 +166,15 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
         for (int s = 0; s < p.n_stages; ++s) {
           const DgStage S = p.st[s];
-          for (int nh = 0; nh < S.n_halves; ++nh) {
-            mbar_wait(bar_empty(stage), phase ^ 1);
-            mbar_arrive_expect_tx(bar_full(stage), S.n_kb * kBlockBytes);
-            bulk_g2s(sbase + C::OFF_RING + stage * C::STAGE_BYTES, p.packed_t + (size_t)(S.block0 + nh * S.n_kb) * kBlockBytes,
-                     S.n_kb * kBlockBytes, bar_full(stage));
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-          }
+          for (int nh = 0; nh < S.n_halves; ++nh)
+            for (int kb0 = 0; kb0 < S.n_kb; kb0 += C::SKB) {
+              const uint32_t bytes = (uint32_t)min(C::SKB, S.n_kb - kb0) * kBlockBytes;
+              mbar_wait(bar_empty(stage), phase ^ 1);
+              mbar_arrive_expect_tx(bar_full(stage), bytes);
+              bulk_g2s(sbase + C::OFF_RING + stage * C::STAGE_BYTES, p.packed_t + (size_t)(S.block0 + nh * S.n_kb + kb0) * kBlockBytes,
+                       bytes, bar_full(stage));
+              if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
         }
     }
     __syncwarp();
@@ -203,27 +208,31 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
             // the chunk after this one: (s, nh+1), else (s+1, 0), else the next tile's first
             const bool last_in_stage = nh + 1 == S.n_halves;
             const bool last_chunk = last_in_stage && s + 1 == p.n_stages;
-            const uint32_t next_stage = (stage + 1 == C::STAGES) ? 0 : stage + 1;
-            const uint32_t next_phase = (stage + 1 == C::STAGES) ? phase ^ 1 : phase;
             const uint32_t need_w = (!last_chunk || more_tiles) ? 1u : 0u;
             const uint32_t need_a0 = (last_in_stage && !last_chunk && p.st[s + 1].a_sel != 2) ? 1u : 0u;
-            const uint32_t b_lo = (((sbase + C::OFF_RING + stage * C::STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
 #pragma unroll
             for (int kb = 0; kb < C::KB; ++kb) {
               if (kb < S.n_kb) {
                 if (waits_a && nh == 0 && (kb & 1) == 0) { ar_par[kb >> 1] ^= 1; tc_fence_after(); }   // half kb/2 of the A operand is there
                 const uint32_t acc0 = (S.first_part && kb == 0) ? 0u : 1u;
-                if (kb + 1 < S.n_kb)
-                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo + ((kb * kBlockBytes) >> 4), desc_hi, idesc, acc0,
+                const uint32_t b_lo = (((sbase + C::OFF_RING + stage * C::STAGE_BYTES + (kb % C::SKB) * kBlockBytes) & 0x3FFFF) >> 4) | (1u << 16);
+                const bool chunk_end = kb + 1 == S.n_kb;
+                const bool stage_end = chunk_end || (kb % C::SKB) == C::SKB - 1;      // last K block read from this ring stage
+                const uint32_t next_stage = (stage + 1 == C::STAGES) ? 0 : stage + 1;
+                const uint32_t next_phase = (stage + 1 == C::STAGES) ? phase ^ 1 : phase;
+                if (!chunk_end)
+                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo, desc_hi, idesc, acc0,
                                          bar_a_ready(((kb + 1) >> 1) & 1), ar_par[((kb + 1) >> 1) & 1],
-                                         (waits_a && nh == 0 && ((kb + 1) & 1) == 0) ? 1u : 0u, bar_full(0), 0u, 0u, bar_acc_full(nh), 0u);
+                                         (waits_a && nh == 0 && ((kb + 1) & 1) == 0) ? 1u : 0u,
+                                         bar_full(next_stage), next_phase, stage_end ? 1u : 0u, bar_acc_full(nh), 0u,
+                                         bar_empty(stage), stage_end ? 1u : 0u, 0u);
                 else
-                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo + ((kb * kBlockBytes) >> 4), desc_hi, idesc, acc0,
+                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo, desc_hi, idesc, acc0,
                                          bar_a_ready(0), ar_par[0], need_a0, bar_full(next_stage), next_phase, need_w,
-                                         bar_acc_full(nh), S.last_part ? 1u : 0u);
+                                         bar_acc_full(nh), S.last_part ? 1u : 0u, bar_empty(stage), 1u, 0u);
+                if (stage_end) { stage = next_stage; phase = next_phase; }
               }
             }
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -235,8 +244,6 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t af_par[2] = {0, 0};
     uint32_t mw_next[2] = {0, 0};                 // mask words of the next masked epilogue, fetched one epilogue ahead
-    const bool releaser = threadIdx.x == 128;     // an active participant frees the ring stages (see mlp_tc.cu)
-    uint32_t rel_stage = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int ray = p.ray_index ? p.ray_index[tile] : tile;
       const uint8_t* sv = p.saved + (size_t)tile * p.saved_blocks * kBlockBytes;
@@ -292,8 +299,6 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
         for (int h = 0; h < S.n_halves; ++h) {
           const int col0 = h * 128 + ch * 64;
           mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
-          if (releaser)
-            for (int r = 0; r < S.parts; ++r) { mbar_arrive(bar_empty(rel_stage)); if (++rel_stage == C::STAGES) rel_stage = 0; }
           tc_fence_after();
           if (S.kind == 3) {
             // input gradient: 64 accumulator columns (the in_dim features), fp32 rows straight to d_features

@@ -133,12 +133,14 @@ __device__ __forceinline__ void umma_ss_conv(uint32_t d_tmem, uint32_t a_lo, uin
 // if the data of the next group is already there - the common case - the thread never stalls with an empty queue
 // behind it; only a failed probe falls into the blocking try_wait loop.  need_x == 0 disables barrier x (pass any valid
 // barrier address).  do_commit: tcgen05.commit -> bar_commit right after the MMAs (before any blocking wait, so the
-// consumer of the accumulator is never held up by this thread's wait).  A_TMEM: A operand from tensor memory (a = TMEM address, +8 columns per K=16 step), else from a
+// consumer of the accumulator is never held up by this thread's wait).  do_release: a second commit that frees the ring
+// stage this K block was the last reader of.  A_TMEM: A operand from tensor memory (a = TMEM address, +8 columns per K=16 step), else from a
 // shared-memory descriptor (a = descriptor lo word, +2 per step); b_lo advances by 2 (32 bytes >> 4) per step.
 template <bool A_TMEM>
 __device__ __forceinline__ void umma_kblock_conv(uint32_t d_tmem, uint32_t a, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
                                                  uint32_t accumulate_first, uint32_t bar_a, uint32_t par_a, uint32_t need_a,
-                                                 uint32_t bar_b, uint32_t par_b, uint32_t need_b, uint32_t bar_commit, uint32_t do_commit) {
+                                                 uint32_t bar_b, uint32_t par_b, uint32_t need_b, uint32_t bar_commit, uint32_t do_commit,
+                                                 uint32_t bar_release, uint32_t do_release, uint32_t release_mask) {
 #define DURF_KB_WAIT(Q, BAR, PAR, L)                                             \
       "@" Q " bra " L "_DONE;\n"                                                  \
       L "_WAIT:\n"                                                                \
@@ -149,12 +151,23 @@ __device__ __forceinline__ void umma_kblock_conv(uint32_t d_tmem, uint32_t a, ui
       "@t bra " L "_WAIT;\n"                                                      \
       "trap;\n"                                                                   \
       L "_DONE:\n"
+  // ring-stage release: the commit arrives on the stage's `empty` barrier once every MMA issued so far (in particular the
+  // ones reading that stage) has completed; release_mask != 0 delivers it to the same barrier of every CTA in the mask
+  // (CTA pairs fill their ring stages jointly by multicast)
+#define DURF_KB_RELEASE                                                                                              \
+      "setp.ne.u32 t, %15, 0;\n and.pred t, t, e;\n"                                                                 \
+      "setp.ne.u32 m, %16, 0;\n and.pred u, t, m;\n"                                                                 \
+      "@u tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%14], mk;\n"      \
+      "not.pred m, m;\n and.pred u, t, m;\n"                                                                         \
+      "@u tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%14];\n"
   if constexpr (A_TMEM) {
     asm volatile(
         "{\n"
-        ".reg .pred e, pacc, ptrue, qa, qb, t;\n"
+        ".reg .pred e, pacc, ptrue, qa, qb, t, m, u;\n"
         ".reg .b64 db;\n"
         ".reg .b32 bl, al, cnt;\n"
+        ".reg .b16 mk;\n"
+        "cvt.u16.u32 mk, %16;\n"
         "mbarrier.test_wait.parity.shared::cta.b64 qa, [%6], %7;\n"
         "mbarrier.test_wait.parity.shared::cta.b64 qb, [%9], %10;\n"
         "elect.sync _|e, 0xffffffff;\n"
@@ -170,19 +183,23 @@ __device__ __forceinline__ void umma_kblock_conv(uint32_t d_tmem, uint32_t a, ui
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [al], db, %4, ptrue;\n"
         "setp.ne.u32 t, %13, 0;\n and.pred t, t, e;\n"
         "@t tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n"
+        DURF_KB_RELEASE
         "setp.eq.u32 t, %8, 0;\n or.pred qa, qa, t;\n"
         "setp.eq.u32 t, %11, 0;\n or.pred qb, qb, t;\n"
         "mov.u32 cnt, 0;\n"
         DURF_KB_WAIT("qa", "%6", "%7", "LA")
         DURF_KB_WAIT("qb", "%9", "%10", "LB")
         "}\n" ::"r"(d_tmem), "r"(a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first), "r"(bar_a), "r"(par_a), "r"(need_a),
-        "r"(bar_b), "r"(par_b), "r"(need_b), "r"(bar_commit), "r"(do_commit) : "memory");
+        "r"(bar_b), "r"(par_b), "r"(need_b), "r"(bar_commit), "r"(do_commit), "r"(bar_release), "r"(do_release), "r"(release_mask)
+        : "memory");
   } else {
     asm volatile(
         "{\n"
-        ".reg .pred e, pacc, ptrue, qa, qb, t;\n"
+        ".reg .pred e, pacc, ptrue, qa, qb, t, m, u;\n"
         ".reg .b64 da, db;\n"
         ".reg .b32 bl, al, cnt;\n"
+        ".reg .b16 mk;\n"
+        "cvt.u16.u32 mk, %16;\n"
         "mbarrier.test_wait.parity.shared::cta.b64 qa, [%6], %7;\n"
         "mbarrier.test_wait.parity.shared::cta.b64 qb, [%9], %10;\n"
         "elect.sync _|e, 0xffffffff;\n"
@@ -198,15 +215,18 @@ __device__ __forceinline__ void umma_kblock_conv(uint32_t d_tmem, uint32_t a, ui
         "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, ptrue;\n"
         "setp.ne.u32 t, %13, 0;\n and.pred t, t, e;\n"
         "@t tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n"
+        DURF_KB_RELEASE
         "setp.eq.u32 t, %8, 0;\n or.pred qa, qa, t;\n"
         "setp.eq.u32 t, %11, 0;\n or.pred qb, qb, t;\n"
         "mov.u32 cnt, 0;\n"
         DURF_KB_WAIT("qa", "%6", "%7", "LA")
         DURF_KB_WAIT("qb", "%9", "%10", "LB")
         "}\n" ::"r"(d_tmem), "r"(a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first), "r"(bar_a), "r"(par_a), "r"(need_a),
-        "r"(bar_b), "r"(par_b), "r"(need_b), "r"(bar_commit), "r"(do_commit) : "memory");
+        "r"(bar_b), "r"(par_b), "r"(need_b), "r"(bar_commit), "r"(do_commit), "r"(bar_release), "r"(do_release), "r"(release_mask)
+        : "memory");
   }
 #undef DURF_KB_WAIT
+#undef DURF_KB_RELEASE
 }
 __device__ __forceinline__ void tc_commit_conv(uint32_t bar) {
   asm volatile(
