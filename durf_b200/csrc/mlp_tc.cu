@@ -380,6 +380,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
             auto gcol = [&](int i) { return SAVE ? col0 + i * 32 : h * 128 + i * 64 + ch * 32; };
             tmem_ld32_issue(t_lane + C::ACC_COL + gcol(0), v[0]);
             release();
+            uint32_t pk[NG][16];
 #pragma unroll
             for (int i = 0; i < NG; ++i) {
               const int cg = gcol(i);
@@ -395,12 +396,11 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
               if (i + 1 < NG) tmem_ld32_issue(t_lane + C::ACC_COL + gcol(i + 1), v[i + 1]);
               if (tr && i == 0) { e_ld += clock64() - eq; eq = clock64(); }
               if (tr) tq1 = clock64();
-              uint32_t pk[16];
               const uint32_t wden_addr = sbase + C::OFF_WDEN + cg * 4;
-              if (kind == 0) epi_pack<0>(v[i], b4, wden_addr, den, pk);
-              else if (kind == 1) epi_pack<1>(v[i], b4, wden_addr, den, pk);
-              else epi_pack<2>(v[i], b4, wden_addr, den, pk);
-              tmem_st16(o_buf + cg / 2, pk);
+              if (kind == 0) epi_pack<0>(v[i], b4, wden_addr, den, pk[i]);
+              else if (kind == 1) epi_pack<1>(v[i], b4, wden_addr, den, pk[i]);
+              else epi_pack<2>(v[i], b4, wden_addr, den, pk[i]);
+              tmem_st16(o_buf + cg / 2, pk[i]);
               if constexpr (!SAVE) {
                 tmem_st_wait();
                 tc_fence_before();
@@ -408,31 +408,41 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
                 if (lane == 0) mbar_arrive(bar_a_ready(2 * h + i));   // K block 2h+i of the next layer's A operand is in TMEM
               }
               if (tr) { if (i == 0) e_m0 += clock64() - tq1; else e_m1 += clock64() - tq1; }
-              if constexpr (SAVE) {
-                // training: the ReLU mask dgrad needs, 1 bit per element (word k of the group holds elements 2k, 2k+1 in its
-                // halves; a non-negative bf16 half h is non-zero iff bit 15 of h + 0x7FFF is set): element 2k -> bit 15-k,
-                // element 2k+1 -> bit 31-k.  dgrad reads 4 bytes per thread and group instead of a 64-byte activation row.
+            }
+            if (tr) { e_math += clock64() - eq; eq = clock64(); }
+            if constexpr (SAVE) {
+              // hand the half over first: nothing of the bookkeeping below may sit between "accumulator complete" and "A operand
+              // of the next layer ready"
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive(bar_a_ready(2 * h));   // half h (K blocks 2h, 2h+1) of the next layer's A operand is in TMEM
+                mbar_arrive(bar_a_ready(2 * h + 1));
+              }
+              if (tr) { e_st += clock64() - eq; eq = clock64(); }
+              // training, off the critical path: (1) the ReLU mask dgrad needs, 1 bit per element (word k of a group holds
+              // elements 2k, 2k+1 in its halves; a non-negative bf16 half is non-zero iff bit 15 of half + 0x7FFF is set):
+              // element 2k -> bit 15-k, element 2k+1 -> bit 31-k; dgrad reads 4 bytes per thread and group instead of a
+              // 64-byte activation row.  (2) the activation itself (A operand of wgrad): the warp's 32 rows x 64 columns are a
+              // contiguous 4 KB piece of the global block image, staged in shared memory in image order and handed to the
+              // bulk-copy engine, so the store to HBM never blocks the epilogue.
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the piece filled two epilogues ago was read
+              __syncwarp();
+              const uint32_t sdst = sbase + C::OFF_STG + ((stg_buf * 8 + (warp - 4)) << 12) + (lane >> 3) * 1024 + (lane & 7) * 128;
+#pragma unroll
+              for (int i = 0; i < NG; ++i) {
                 if (kind != 2) {
                   uint32_t mw = 0;
 #pragma unroll
-                  for (int k = 0; k < 16; ++k) mw |= ((pk[k] + 0x7FFF7FFFu) >> k) & (0x80008000u >> k);
-                  if (valid) p.masks[(((size_t)tile * p.depth + g) * (W / 32) + (cg >> 5)) * 128 + row] = mw;
+                  for (int k = 0; k < 16; ++k) mw |= ((pk[i][k] + 0x7FFF7FFFu) >> k) & (0x80008000u >> k);
+                  if (valid) p.masks[(((size_t)tile * p.depth + g) * (W / 32) + ((col0 + i * 32) >> 5)) * 128 + row] = mw;
                 }
-                // ... and the activation itself (A operand of wgrad).  The warp's 32 rows x 64 columns
-                // are a contiguous 4 KB piece of the global block image: stage it in shared memory in image order ...
-                if (i == 0) {
-                  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the piece filled two epilogues ago was read
-                  __syncwarp();
-                }
-                const uint32_t sdst = sbase + C::OFF_STG + ((stg_buf * 8 + (warp - 4)) << 12) + (lane >> 3) * 1024 + (lane & 7) * 128;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4)
                   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + (((uint32_t)(i * 4 + q4) ^ (lane & 7)) << 4)),
-                               "r"(pk[4 * q4]), "r"(pk[4 * q4 + 1]), "r"(pk[4 * q4 + 2]), "r"(pk[4 * q4 + 3]) : "memory");
+                               "r"(pk[i][4 * q4]), "r"(pk[i][4 * q4 + 1]), "r"(pk[i][4 * q4 + 2]), "r"(pk[i][4 * q4 + 3]) : "memory");
               }
-            }
-            if constexpr (SAVE) {
-              // ... and hand it to the bulk-copy engine: the store to HBM never blocks the epilogue
               __syncwarp();
               asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               if (lane == 0) {
@@ -443,18 +453,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               }
               stg_buf ^= 1;
+              if (tr) e_math += clock64() - eq;
             }
-            if (tr) { e_math += clock64() - eq; eq = clock64(); }
-            if constexpr (SAVE) {
-              tmem_st_wait();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                mbar_arrive(bar_a_ready(2 * h));   // half h (K blocks 2h, 2h+1) of the next layer's A operand is in TMEM
-                mbar_arrive(bar_a_ready(2 * h + 1));
-              }
-            }
-            if (tr) e_st += clock64() - eq;
           } else {
             // condition layer: + per-ray bias, ReLU, partial rgb head over this warp's columns
 #pragma unroll
