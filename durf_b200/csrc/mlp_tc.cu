@@ -370,6 +370,35 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
           auto release = [&]() {      // the input tile is free once the last layer reading it has completed
             if (releaser && rel_inp && h == n_halves - 1) mbar_arrive(bar_inp_empty);
           };
+          // training: one warp's 32 rows x 64 columns of a saved activation (and their 1-bit ReLU mask words)
+          auto save_piece = [&](const uint32_t (&pk)[NG][16], bool with_mask) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the piece filled two epilogues ago was read
+            __syncwarp();
+            const uint32_t sdst = sbase + C::OFF_STG + ((stg_buf * 8 + (warp - 4)) << 12) + (lane >> 3) * 1024 + (lane & 7) * 128;
+#pragma unroll
+            for (int i = 0; i < NG; ++i) {
+              if (with_mask) {
+                uint32_t mw = 0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) mw |= ((pk[i][k] + 0x7FFF7FFFu) >> k) & (0x80008000u >> k);
+                if (valid) p.masks[(((size_t)tile * p.depth + g) * (W / 32) + ((col0 + i * 32) >> 5)) * 128 + row] = mw;
+              }
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + (((uint32_t)(i * 4 + q4) ^ (lane & 7)) << 4)),
+                             "r"(pk[i][4 * q4]), "r"(pk[i][4 * q4 + 1]), "r"(pk[i][4 * q4 + 2]), "r"(pk[i][4 * q4 + 3]) : "memory");
+            }
+            __syncwarp();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (lane == 0) {
+              uint8_t* gdst = p.saved + ((size_t)tile * p.saved_blocks_per_tile + g * C::KB + (col0 >> 6)) * kBlockBytes + q * 4096;
+              if (valid)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(gdst),
+                             "r"(sbase + C::OFF_STG + ((stg_buf * 8 + (warp - 4)) << 12)) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            stg_buf ^= 1;
+          };
           uint32_t v[NG][32];
           if (kind != 3) {
             // software pipeline over two 32-column groups: the TMEM load of group 1 and the bias fetches run
@@ -427,32 +456,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
               // 64-byte activation row.  (2) the activation itself (A operand of wgrad): the warp's 32 rows x 64 columns are a
               // contiguous 4 KB piece of the global block image, staged in shared memory in image order and handed to the
               // bulk-copy engine, so the store to HBM never blocks the epilogue.
-              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the piece filled two epilogues ago was read
-              __syncwarp();
-              const uint32_t sdst = sbase + C::OFF_STG + ((stg_buf * 8 + (warp - 4)) << 12) + (lane >> 3) * 1024 + (lane & 7) * 128;
-#pragma unroll
-              for (int i = 0; i < NG; ++i) {
-                if (kind != 2) {
-                  uint32_t mw = 0;
-#pragma unroll
-                  for (int k = 0; k < 16; ++k) mw |= ((pk[i][k] + 0x7FFF7FFFu) >> k) & (0x80008000u >> k);
-                  if (valid) p.masks[(((size_t)tile * p.depth + g) * (W / 32) + ((col0 + i * 32) >> 5)) * 128 + row] = mw;
-                }
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4)
-                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdst + (((uint32_t)(i * 4 + q4) ^ (lane & 7)) << 4)),
-                               "r"(pk[i][4 * q4]), "r"(pk[i][4 * q4 + 1]), "r"(pk[i][4 * q4 + 2]), "r"(pk[i][4 * q4 + 3]) : "memory");
-              }
-              __syncwarp();
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              if (lane == 0) {
-                uint8_t* gdst = p.saved + ((size_t)tile * p.saved_blocks_per_tile + g * C::KB + (col0 >> 6)) * kBlockBytes + q * 4096;
-                if (valid)
-                  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(gdst),
-                               "r"(sbase + C::OFF_STG + ((stg_buf * 8 + (warp - 4)) << 12)) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              }
-              stg_buf ^= 1;
+              save_piece(pk, kind != 2);
               if (tr) e_math += clock64() - eq;
             }
           } else {
@@ -467,6 +471,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_a_ready(2 * h));   // accumulators drained: the next tile's first layer may overwrite them
             const uint32_t svb = sbase + C::OFF_VBIAS + col0 * 4, swr = sbase + C::OFF_WRGB + col0 * 4;
+            uint32_t pkc[NG][16];
 #pragma unroll
             for (int i = 0; i < NG; ++i)
 #pragma unroll
@@ -479,13 +484,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
                 rgb[0] = fmaf(a0, w0.x, rgb[0]); rgb[0] = fmaf(a1, w0.y, rgb[0]); rgb[0] = fmaf(a2, w0.z, rgb[0]); rgb[0] = fmaf(a3, w0.w, rgb[0]);
                 rgb[1] = fmaf(a0, w1.x, rgb[1]); rgb[1] = fmaf(a1, w1.y, rgb[1]); rgb[1] = fmaf(a2, w1.z, rgb[1]); rgb[1] = fmaf(a3, w1.w, rgb[1]);
                 rgb[2] = fmaf(a0, w2.x, rgb[2]); rgb[2] = fmaf(a1, w2.y, rgb[2]); rgb[2] = fmaf(a2, w2.z, rgb[2]); rgb[2] = fmaf(a3, w2.w, rgb[2]);
-                if (SAVE && valid) {
-                  const int cc = col0 + c;
-                  uint8_t* blk = p.saved + ((size_t)tile * p.saved_blocks_per_tile + g * C::KB + (cc >> 6)) * kBlockBytes;
-                  *reinterpret_cast<uint2*>(blk + sw128_offset(row, (cc & 63) >> 3) + (cc & 7) * 2) =
-                      make_uint2(cvt_bf16x2(a0, a1), cvt_bf16x2(a2, a3));
-                }
+                if (SAVE) { pkc[i][2 * j] = cvt_bf16x2(a0, a1); pkc[i][2 * j + 1] = cvt_bf16x2(a2, a3); }
               }
+            if constexpr (SAVE) save_piece(pkc, false);    // the condition layer's activation (wgrad operand; its mask is read from it)
           }
         }
       }
