@@ -521,17 +521,31 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
 __global__ void __launch_bounds__(128)
 cond_bias_kernel(int M, const int32_t* __restrict__ count, const int32_t* __restrict__ ray_index, const float* __restrict__ cond,
                  int cond_dim, const float* __restrict__ w_view, const float* __restrict__ b_cond, float* __restrict__ vbias) {
+  constexpr int RB = 16;                      // rays per block iteration: their view encodings are staged in shared memory once
   __shared__ float s_w[64 * 128];
+  __shared__ float s_c[RB][64];
   const int n = count ? min(*count, M) : M;
   for (int i = threadIdx.x; i < cond_dim * 128; i += blockDim.x) s_w[i] = w_view[i];
-  __syncthreads();
   const int j = threadIdx.x;
   const float b = b_cond[j];
-  for (int m = blockIdx.x; m < n; m += gridDim.x) {
-    const float* cv = cond + (size_t)(ray_index ? ray_index[m] : m) * cond_dim;
-    float vb = b;
-    for (int i = 0; i < cond_dim; ++i) vb = fmaf(cv[i], s_w[i * 128 + j], vb);
-    vbias[(size_t)m * 128 + j] = vb;
+  for (int m0 = blockIdx.x * RB; m0 < n; m0 += gridDim.x * RB) {
+    __syncthreads();                          // s_w ready / previous iteration's s_c consumed
+    for (int i = threadIdx.x; i < RB * cond_dim; i += blockDim.x) {
+      const int r = i / cond_dim, c = i - r * cond_dim, m = m0 + r;
+      s_c[r][c] = m < n ? cond[(size_t)(ray_index ? ray_index[m] : m) * cond_dim + c] : 0.f;
+    }
+    __syncthreads();
+    float vb[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) vb[r] = b;
+    for (int i = 0; i < cond_dim; ++i) {      // same summation order per output as a ray-at-a-time loop
+      const float w = s_w[i * 128 + j];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) vb[r] = fmaf(s_c[r][i], w, vb[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+      if (m0 + r < n) vbias[(size_t)(m0 + r) * 128 + j] = vb[r];
   }
 }
 
@@ -680,7 +694,7 @@ int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a) {
   P.masks = P.saved ? reinterpret_cast<uint32_t*>(P.saved + (size_t)a.M * P.saved_blocks_per_tile * kBlockBytes) : nullptr;
   {
     MlpLayout L(t);
-    const int grid_b = a.M < 148 * 8 ? a.M : 148 * 8;
+    const int grid_b = (a.M + 15) / 16 < 148 * 8 ? (a.M + 15) / 16 : 148 * 8;
     cond_bias_kernel<<<grid_b, 128, 0, st>>>(a.M, a.count, a.ray_index, a.cond, t.cond_dim,
                                              a.params + L.w_off[t.depth + 2] + (size_t)t.width * t.cond_width,
                                              a.params + L.b_off[t.depth + 2], (float*)a.workspace);
