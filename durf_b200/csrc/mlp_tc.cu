@@ -380,7 +380,11 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
               if (with_mask) {
                 uint32_t mw = 0;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) mw |= ((pk[i][k] + 0x7FFF7FFFu) >> k) & (0x80008000u >> k);
+                for (int k = 0; k < 16; ++k) {     // HSET2: 0xFFFF per half that is > 0, then one LOP3 picks the word's two bits
+                  uint32_t gt;
+                  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(gt) : "r"(pk[i][k]), "r"(0u));
+                  mw |= gt & (0x80008000u >> k);
+                }
                 if (valid) p.masks[(((size_t)tile * p.depth + g) * (W / 32) + ((col0 + i * 32) >> 5)) * 128 + row] = mw;
               }
 #pragma unroll
