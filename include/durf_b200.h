@@ -170,7 +170,9 @@ typedef struct DurfMlpArgs {
   int32_t accumulate;       /* 0: write, 1: add into raw_rgb/raw_density (object MLPs, obbpose_model.py:203-204,233-234) */
   float* raw_rgb;           /* [B,N,3] */
   float* raw_density;       /* [B,N] */
-  void* saved;              /* [opt] activations kept for the backward pass (durf_mlp_saved_bytes) */
+  void* saved;              /* [opt] kept for the backward pass (durf_mlp_saved_bytes): FP32 the layer outputs; BF16 every
+                               layer's bf16 activations as tile images followed by the trunk layers' 1-bit ReLU masks.  The
+                               backward call must pass the same buffer with the same M. */
   void* workspace;
   size_t workspace_bytes;
 } DurfMlpArgs;
