@@ -39,7 +39,7 @@ class DurfError(RuntimeError):
 
 class Camera(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("focal", C.c_float), ("c2w", C.c_float * 12),
-                ("near", C.c_float), ("far", C.c_float)]
+                ("near", C.c_float), ("far", C.c_float), ("use_principal_point", C.c_int32), ("cx", C.c_float), ("cy", C.c_float)]
 
 
 class MlpTopology(C.Structure):

@@ -1,6 +1,6 @@
 // N2 -- pinhole ray generation on the device (the reference builds its rays on the host with numpy:
 // Carla/Waymo._generate_rays_multi, internal/obbpose_dataset.py:613-661).  One thread per pixel:
-//   camera_dir = ((x - W/2)/f, -(y - H/2)/f, -1);  direction_i = sum_j camera_dir_j * c2w[i][j]  (un-normalised);
+//   camera_dir = ((x - cx)/f, -(y - cy)/f, -1) with (cx, cy) = (W/2, H/2) (Carla) or the file's principal point (Waymo, :1882-1885);  direction_i = sum_j camera_dir_j * c2w[i][j]  (un-normalised);
 //   origin = c2w[:, 3];  viewdir = direction / |direction|;
 //   radius = |direction(y) - direction(y+1)| * 2 / sqrt(12); the last row reuses the spacing |dir(H-3) - dir(H-2)|, which is
 //   what `np.concatenate([v, v[-2:-1, :]], 0)` appends (:640-646).
@@ -12,13 +12,14 @@ namespace durf {
 struct RayGenParams {
   int W, H, row0, row1;
   float focal, near, far;
+  float pcx, pcy;            // principal point in pixels
   float c2w[12];
   float* origins; float* directions; float* viewdirs; float* radii; float* lossmult; float* near_out; float* far_out;
 };
 
 __device__ __forceinline__ void world_dir(const RayGenParams& p, float x, float y, float (&d)[3]) {
-  const float cx = (x - (float)p.W * 0.5f) / p.focal;
-  const float cy = -(y - (float)p.H * 0.5f) / p.focal;
+  const float cx = (x - p.pcx) / p.focal;
+  const float cy = -(y - p.pcy) / p.focal;
   const float cz = -1.f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) d[i] = (cx * p.c2w[4 * i] + cy * p.c2w[4 * i + 1]) + cz * p.c2w[4 * i + 2];
@@ -64,6 +65,8 @@ extern "C" int durf_generate_rays(durf_stream_t stream, const DurfCamera* cam, i
   DURF_REQUIRE(origins && directions && viewdirs && radii && lossmult && near && far, DURF_E_INVALID, "durf_generate_rays: null buffer");
   RayGenParams p;
   p.W = cam->width; p.H = cam->height; p.row0 = row0; p.row1 = row1; p.focal = cam->focal; p.near = cam->near; p.far = cam->far;
+  p.pcx = cam->use_principal_point ? cam->cx : (float)cam->width * 0.5f;
+  p.pcy = cam->use_principal_point ? cam->cy : (float)cam->height * 0.5f;
   for (int i = 0; i < 12; ++i) p.c2w[i] = cam->c2w[i];
   p.origins = origins; p.directions = directions; p.viewdirs = viewdirs; p.radii = radii; p.lossmult = lossmult; p.near_out = near; p.far_out = far;
   const int64_t n = (int64_t)(row1 - row0) * cam->width;

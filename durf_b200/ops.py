@@ -40,14 +40,18 @@ def reset_launch_count() -> None:
 
 
 # ---- N2: ray generation on the device ------------------------------------------------------------------
-def generate_rays(c2w, width: int, height: int, focal: float, near: float, far: float, row0: int = 0, row1=None, device='cuda'):
+def generate_rays(c2w, width: int, height: int, focal: float, near: float, far: float, row0: int = 0, row1=None, device='cuda',
+                  principal_point=None):
     """Rays of the pixel rows [row0,row1) of one pinhole camera as a `utils.Rays` tuple of CUDA tensors
-    (obbpose_dataset.py:613-661; [n,3] x3 and [n,1] x4 like the reference's flattened BoxRays)."""
+    (obbpose_dataset.py:613-661; [n,3] x3 and [n,1] x4 like the reference's flattened BoxRays).  `principal_point` =
+    (cx, cy) in pixels selects the Waymo loader's variant (:1868-1917); None = image centre (Carla)."""
     import numpy as np
     from .utils import Rays
     row1 = height if row1 is None else row1
     n = (row1 - row0) * width
     cam = L.Camera(width=width, height=height, focal=float(focal), near=float(near), far=float(far))
+    if principal_point is not None:
+        cam.use_principal_point, cam.cx, cam.cy = 1, float(principal_point[0]), float(principal_point[1])
     flat = np.asarray(c2w, np.float32)[:3, :4].reshape(-1)
     for i in range(12):
         cam.c2w[i] = float(flat[i])

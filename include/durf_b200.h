@@ -100,8 +100,11 @@ typedef struct DurfCamera {
   float focal;             /* pixels */
   float c2w[12];           /* camera-to-world [3,4], row-major (HOST values) */
   float near, far;
+  int32_t use_principal_point; /* 0: image centre (width/2, height/2), the Carla loader (obbpose_dataset.py:627-629);
+                                  1: (cx, cy) below, the Waymo loader (obbpose_dataset.py:1863, 1882-1885) */
+  float cx, cy;            /* pixels */
 } DurfCamera;
-/* Carla/Waymo._generate_rays_multi (internal/obbpose_dataset.py:613-661) for the pixel rows [row0,row1) of one camera,
+/* Carla/Waymo._generate_rays_multi (internal/obbpose_dataset.py:613-661, 1868-1917) for the pixel rows [row0,row1) of one camera,
  * row-major: origins, directions (un-normalised), viewdirs [n,3]; radii, lossmult (=1), near, far [n]; n = (row1-row0)*width.
  * `cam` is a HOST pointer (read during the call). */
 int durf_generate_rays(durf_stream_t stream, const DurfCamera* cam, int32_t row0, int32_t row1, float* origins,

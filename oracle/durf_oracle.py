@@ -774,14 +774,16 @@ def adam_step(params: Sequence[Tensor], grads: Sequence[Tensor], m: Sequence[Ten
 # internal/obbpose_dataset.py : pinhole ray generation (numpy on the host in the reference)
 # --------------------------------------------------------------------------------------
 
-def generate_rays(c2w: np.ndarray, w: int, h: int, focal: float, near: float, far: float):
+def generate_rays(c2w: np.ndarray, w: int, h: int, focal: float, near: float, far: float, principal_point=None):
     """reference internal/obbpose_dataset.py:613-661 (`_generate_rays_multi`) for one camera, in float32 like the
     reference's arrays (numpy 1.x value-based casting keeps `v * 2 / np.sqrt(12)` in float32).
+    `principal_point` = (cx, cy): the Waymo loader's variant (:1868-1917), which differs only in the pixel offset.
     Returns Rays of numpy arrays shaped [h, w, 3] / [h, w, 1]."""
     f32 = np.float32
     c2w = np.asarray(c2w, f32)
     x, y = np.meshgrid(np.arange(w, dtype=f32), np.arange(h, dtype=f32), indexing='xy')
-    cam_dirs = np.stack([(x - f32(w) * f32(0.5)) / f32(focal), -(y - f32(h) * f32(0.5)) / f32(focal), -np.ones_like(x)], axis=-1)
+    pcx, pcy = (f32(w) * f32(0.5), f32(h) * f32(0.5)) if principal_point is None else (f32(principal_point[0]), f32(principal_point[1]))
+    cam_dirs = np.stack([(x - pcx) / f32(focal), -(y - pcy) / f32(focal), -np.ones_like(x)], axis=-1)
     directions = (cam_dirs[..., None, :] * c2w[:3, :3]).sum(axis=-1).astype(f32)
     origins = np.broadcast_to(c2w[:3, -1], directions.shape).astype(f32)
     viewdirs = (directions / np.linalg.norm(directions, axis=-1, keepdims=True)).astype(f32)

@@ -393,6 +393,11 @@ def test_generate_rays_matches_oracle_bit_exact():
         got = ops.generate_rays(c2w, w, h, f, 0.5, 200.0)
         for a, b, name in zip(got, want, O.Rays._fields):
             assert torch.equal(a.cpu().reshape(-1), torch.from_numpy(np.ascontiguousarray(b)).reshape(-1)), name
+        pp = (w * 0.5 + 3.25, h * 0.5 - 1.75)                                        # Waymo variant: explicit principal point
+        want_pp = O.generate_rays(c2w, w, h, f, 0.5, 200.0, principal_point=pp)
+        got_pp = ops.generate_rays(c2w, w, h, f, 0.5, 200.0, principal_point=pp)
+        for a, b, name in zip(got_pp, want_pp, O.Rays._fields):
+            assert torch.equal(a.cpu().reshape(-1), torch.from_numpy(np.ascontiguousarray(b)).reshape(-1)), "principal point: " + name
         part = ops.generate_rays(c2w, w, h, f, 0.5, 200.0, row0=h - 3, row1=h)       # a row range incl. the last row
         assert torch.equal(part.radii.cpu().reshape(-1), torch.from_numpy(want.radii[h - 3:]).reshape(-1))
     empty = ops.generate_rays(c2w, 8, 8, 10.0, 0.0, 1.0, row0=4, row1=4)
