@@ -340,10 +340,10 @@ def render_image(render_fn, rays: Rays, init, ext, ts, rng, alpha, chunk: int = 
 
 
 def render_camera(render_fn, c2w, width: int, height: int, focal: float, near: float, far: float, init, ext, ts, rng, alpha,
-                  chunk: int = 65536):
+                  chunk: int = 65536, principal_point=None):
     """`render_image` for a pinhole camera whose rays are generated ON THE DEVICE (durf_generate_rays, the restatement of
-    obbpose_dataset.py:613-661): no per-ray host->device traffic at all.  Chunks are whole image rows; returns the fine
-    level's (rgb[H,W,3], distance[H,W], acc[H,W]) on the device."""
+    obbpose_dataset.py:613-661; `principal_point` selects the Waymo variant, :1868-1917): no per-ray host->device traffic at
+    all.  Chunks are whole image rows; returns the fine level's (rgb[H,W,3], distance[H,W], acc[H,W]) on the device."""
     dev = torch.device('cuda')
     rows_per_chunk = max(1, chunk // width)
     rgb = torch.empty(height * width, 3, device=dev)
@@ -351,7 +351,7 @@ def render_camera(render_fn, c2w, width: int, height: int, focal: float, near: f
     acc = torch.empty(height * width, device=dev)
     for r0 in range(0, height, rows_per_chunk):
         r1 = min(height, r0 + rows_per_chunk)
-        rays = ops.generate_rays(c2w, width, height, focal, near, far, r0, r1, device=dev)
+        rays = ops.generate_rays(c2w, width, height, focal, near, far, r0, r1, device=dev, principal_point=principal_point)
         out = render_fn(rng, dict(rays=rays, init=init, ext=ext, ts=ts, alpha=alpha))[-1]
         i, n = r0 * width, (r1 - r0) * width
         rgb[i:i + n] = out[0]; dist[i:i + n] = out[1]; acc[i:i + n] = out[2]
