@@ -1,4 +1,4 @@
-// PTX wrappers shared by the tcgen05 kernels (mlp_tc.cu forward, mlp_tc_bwd.cu dgrad / wgrad): mbarriers, bulk copies,
+// PTX wrappers shared by the tcgen05 kernels (mlp_tc.cu forward, mlp_tc_dgrad.cu, mlp_tc_wgrad.cu): mbarriers, bulk copies,
 // tcgen05.mma / ld / st / commit, shared-memory matrix descriptors.  sm_100a only.
 #pragma once
 
@@ -58,61 +58,13 @@ __device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask) : "memory");
 }
-// arrive on the mbarrier at the same offset in CTA `cta` of the cluster (relaxed: with .release the arriving thread stalls
-// ~1000 cycles; the data hazard - the peer's next fill of a ring stage this CTA's MMAs have finished reading - is ordered
-// by the tcgen05.commit that preceded the arrive)
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
-  asm volatile(
-      "{\n"
-      ".reg .b32 ra;\n"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n"
-      "}\n" ::"r"(bar), "r"(cta) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 // Shared-memory matrix descriptors are passed as (lo, hi) words: hi is constant (SBO, version, swizzle), lo holds the
 // start address >> 4, so stepping through K blocks is a 32-bit add.
-// D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 inputs, fp32 accumulate)
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .b64 da, db;\n"
-      "setp.ne.b32 p, %5, 0;\n"
-      "mov.b64 da, {%1, %3};\n"
-      "mov.b64 db, {%2, %3};\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
-      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]: A is 128 lanes (rows) x 8 columns of packed bf16 pairs per K=16 step
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .b64 db;\n"
-      "setp.ne.b32 p, %5, 0;\n"
-      "mov.b64 db, {%2, %3};\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
-      "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
-}
 // Warp-converged variants: ALL lanes of the issuing warp execute the statement with identical operands, the instruction
 // itself is predicated on elect.sync.  Keeping the control flow uniform lets ptxas hold descriptors in uniform registers
 // instead of re-broadcasting them (R2UR) for every instruction.
-__device__ __forceinline__ void umma_ts_conv(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, e;\n"
-      ".reg .b64 db;\n"
-      "elect.sync _|e, 0xffffffff;\n"
-      "setp.ne.b32 p, %5, 0;\n"
-      "mov.b64 db, {%2, %3};\n"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
-      "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void umma_ss_conv(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
