@@ -58,3 +58,27 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+
+
+def test_size_queries_are_host_functions_and_consistent():
+    """durf_mlp_*_bytes are pure host arithmetic (callable without a GPU).  Tensor-core training keeps per ray-level every
+    layer's bf16 activations as 16 KB block images plus the trunk layers' 1-bit ReLU masks (4 bytes per row and 32-column
+    group); an unsupported topology reports 0 (the caller must then use the fp32 path)."""
+    import ctypes as C
+    from durf_b200 import _lib
+    lib = _lib.load()
+    bg = _lib.MlpTopology(60, 256, 8, 4, 27, 128)
+    obj = _lib.MlpTopology(63, 128, 8, 4, 27, 128)
+    for t, width in ((bg, 256), (obj, 128)):
+        blocks = (8 + 1) * (width // 64) + 128 // 64
+        for M in (0, 1, 300):
+            want = M * blocks * 16384 + M * 8 * (width // 32) * 128 * 4
+            assert lib.durf_mlp_saved_bytes(C.byref(t), _lib.PREC_BF16, M, 128) == want
+            # backward workspace = the dZ tile records, same shape as the saved activations
+            assert lib.durf_mlp_workspace_bytes(C.byref(t), _lib.PREC_BF16, M, 128, 1) == M * blocks * 16384
+            # inference workspace = the per-tile view bias [M,128] fp32
+            assert lib.durf_mlp_workspace_bytes(C.byref(t), _lib.PREC_BF16, M, 128, 0) == M * 128 * 4
+        assert lib.durf_mlp_packed_bytes(C.byref(t)) > 0
+    odd = _lib.MlpTopology(60, 192, 8, 4, 27, 128)          # width the tensor-core path does not implement
+    assert lib.durf_mlp_saved_bytes(C.byref(odd), _lib.PREC_BF16, 4, 128) == 0
+    assert lib.durf_mlp_saved_bytes(C.byref(odd), _lib.PREC_FP32, 4, 128) > 0
