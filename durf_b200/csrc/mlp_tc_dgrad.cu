@@ -78,9 +78,10 @@ struct DgCfg {
 };
 
 // Masking / packing of one 32-column group, specialised per stage kind (0: linear, 1: + density term and mask, 2: mask)
-// so the unrolled body is branch-free.  Returns the packed words (bf16 pairs) of the group.
+// so the unrolled body is branch-free.  Writes the group's 64 bytes of the dZ tile image row and returns the packed words.
 template <int KIND>
-__device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], uint32_t mw, float gden, uint32_t wden_addr, uint32_t (&pk)[16]);
+__device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], uint32_t mw, float gden, uint32_t wden_addr,
+                                        uint32_t stage_row, uint32_t r7, int chunk0, uint32_t (&pk)[16]);
 
 // keep a packed bf16 pair where the matching activation halfwords are non-zero (ReLU outputs are +0 or positive)
 __device__ __forceinline__ uint32_t mask_pair(uint32_t packed, uint32_t act) {
@@ -97,7 +98,8 @@ __device__ __forceinline__ uint32_t mask_pair_bits(uint32_t packed, uint32_t mw,
 }
 
 template <int KIND>
-__device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], uint32_t mw, float gden, uint32_t wden_addr, uint32_t (&pk)[16]) {
+__device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], uint32_t mw, float gden, uint32_t wden_addr,
+                                        uint32_t stage_row, uint32_t r7, int chunk0, uint32_t (&pk)[16]) {
 #pragma unroll
   for (int c8 = 0; c8 < 4; ++c8) {
 #pragma unroll
@@ -112,6 +114,11 @@ __device__ __forceinline__ void dg_pack(const uint32_t (&v)[32], uint32_t mw, fl
       pk[c8 * 4 + e] = pr;
     }
   }
+  // the row's 64 bytes go to the warp's staging piece (image order), from where one bulk store takes them to HBM
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (((uint32_t)(chunk0 + q4) ^ r7) << 4)), "r"(pk[4 * q4]),
+                 "r"(pk[4 * q4 + 1]), "r"(pk[4 * q4 + 2]), "r"(pk[4 * q4 + 3]) : "memory");
 }
 
 template <int W>
@@ -310,32 +317,25 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
           uint32_t v[32];
           tmem_ld32_issue(t_lane + C::ACC_COL + col0, v);
           const uint32_t mw[2] = {mw_next[0], mw_next[1]};
-          uint32_t pk[2][16];
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // previous dZ piece was read out
+          __syncwarp();
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             tmem_ld_wait();
             tmem_ld_pin(v);
+            uint32_t pk[16];
             const uint32_t wden_addr = sbase + C::OFF_WDEN + (col0 + i * 32) * 4;
-            if (S.kind == 0) dg_pack<0>(v, mw[i], gden, wden_addr, pk[i]);
-            else if (S.kind == 1) dg_pack<1>(v, mw[i], gden, wden_addr, pk[i]);
-            else dg_pack<2>(v, mw[i], gden, wden_addr, pk[i]);
+            if (S.kind == 0) dg_pack<0>(v, mw[i], gden, wden_addr, my_out + row_off, r7, i * 4, pk);
+            else if (S.kind == 1) dg_pack<1>(v, mw[i], gden, wden_addr, my_out + row_off, r7, i * 4, pk);
+            else dg_pack<2>(v, mw[i], gden, wden_addr, my_out + row_off, r7, i * 4, pk);
             if (i == 0) tmem_ld32_issue(t_lane + C::ACC_COL + col0 + 32, v);
-            if (feeds_next) tmem_st16(o_buf + (col0 + i * 32) / 2, pk[i]);
-            if (W == 128 && S.to_skip) tmem_st16(t_lane + C::ACT_COL + 2 * (W / 2) + (col0 + i * 32) / 2, pk[i]);
+            if (feeds_next) tmem_st16(o_buf + (col0 + i * 32) / 2, pk);
+            if (W == 128 && S.to_skip) tmem_st16(t_lane + C::ACT_COL + 2 * (W / 2) + (col0 + i * 32) / 2, pk);
           }
           if (feeds_next || S.to_skip) tmem_st_wait();
           tc_fence_before();
           mbar_arrive(bar_a_ready(h));     // next stage's A operand half is in TMEM (last stage: accumulators drained)
-          // off the critical path: stage the dZ piece (the row's 2 x 64 bytes in image order) and publish it with one bulk
-          // store, fetch the next epilogue's mask words
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // previous dZ piece was read out
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_out + row_off + (((uint32_t)(i * 4 + q4) ^ r7) << 4)),
-                           "r"(pk[i][4 * q4]), "r"(pk[i][4 * q4 + 1]), "r"(pk[i][4 * q4 + 2]), "r"(pk[i][4 * q4 + 3]) : "memory");
+          // off the critical path: publish the dZ piece, fetch the next epilogue's mask piece
           __syncwarp();
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           if (lane == 0) {
