@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json configs[3] (C4): dynamic scene graph -- background + 8 per-object NeRFs, per-ray OBB intersection and
-merged compositing over Waymo-shape frames.  Times one 1920x1280 frame (rays generated on the device) and checks a
-sub-sample against the oracle (PSNR).  Usage: python tools/c4_scene_graph.py [rows]"""
+merged compositing over Waymo-shape frames.  Times one 1920x1280 frame (rays generated on the device) and reports the share
+of rays that hit a box (parity of this path: tests/test_gpu_model.py).  Usage: python tools/c4_scene_graph.py [rows]"""
 import os
 import sys
 import time
