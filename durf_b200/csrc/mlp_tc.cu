@@ -7,11 +7,15 @@
 //     relu(acc + bias) to bf16 and writes it back to TMEM with tcgen05.st, and the next layer's tcgen05.mma takes its
 //     A operand straight from TMEM (".ts" form).  Two activation buffers alternate by layer, so shared memory is free
 //     for a deep ring of weight chunks;
-//   * every layer is issued as two N-halves.  The epilogue of half 0 runs while the tensor core computes half 1, and
-//     the next layer starts on the K blocks produced by half 0 while the epilogue of half 1 is still running, so the
-//     tensor pipe only waits for an epilogue if that epilogue is slower than half a layer of MMAs.
+//   * every layer is issued as two N-halves.  The epilogue of half 0 runs while the tensor core computes half 1, and the
+//     epilogue hands the next layer's A operand over per 64-column K block, so the next layer starts on the blocks of half 0
+//     while the epilogue of half 1 is still packing;
+//   * the MMA issuer never executes a wait between two groups of MMAs (a wait there drains the tensor queue): every K block
+//     probes the barriers of the NEXT K block before its own MMAs and consumes the outcome after them (umma_kblock_conv),
+//     and the same asm block carries the tcgen05.commit's (accumulator ready, ring stage free).
 // Warp roles (384 threads): warp 0 = weight producer (cp.async.bulk of pre-tiled, pre-swizzled bf16 chunks into an
-// mbarrier ring), warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator + feature-tile loader, warp 3 idle,
+// mbarrier ring; in a CTA pair each CTA fetches half of a stage and multicasts it), warp 1 = MMA issuer (whole warp walks
+// the schedule, one elected lane issues), warp 2 = TMEM allocator + feature-tile loader, warp 3 idle,
 // warps 4-11 = epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter split the columns of a half).
 // The skip connection (obbpose_model.py:332-333) is an extra K block read from the still-resident input tile (smem,
 // ".ss" form); the view direction (constant along a ray) enters the condition layer as a per-tile fp32 bias
