@@ -149,6 +149,14 @@ composite_bwd_kernel(const DurfCompositeArgs a, const float* __restrict__ d_comp
   float before = warp_scan_excl(run, lane);
   float w[kSPL], trans[kSPL], alpha[kSPL], gw[kSPL], sig[kSPL][3];
   float gwsum = 0.f;
+  float gin[kSPL];                                                 // dL/dweights of this lane's samples (one 16-byte load at N = 128)
+  if (N == 128) {
+    const float4 g4 = *reinterpret_cast<const float4*>(d_weights + (size_t)ray * N + n0);
+    gin[0] = g4.x; gin[1] = g4.y; gin[2] = g4.z; gin[3] = g4.w;
+  } else {
+#pragma unroll
+    for (int q = 0; q < kSPL; ++q) gin[q] = (n0 + q < N) ? d_weights[(size_t)ray * N + n0 + q] : 0.f;
+  }
 #pragma unroll
   for (int q = 0; q < kSPL; ++q) {
     const bool ok = n0 + q < N;
@@ -158,7 +166,7 @@ composite_bwd_kernel(const DurfCompositeArgs a, const float* __restrict__ d_comp
     const float raw_w = alpha[q] * trans[q];
     const bool finite = (raw_w == raw_w) && !isinf(raw_w);
     w[q] = ok ? nan_to_num(raw_w) : 0.f;
-    float g = ok ? d_weights[(size_t)ray * N + n0 + q] : 0.f;
+    float g = gin[q];
 #pragma unroll
     for (int c = 0; c < 3; ++c) { sig[q][c] = a.activated ? r.rgb[q][c] : sigmoidf(r.rgb[q][c]); g += gc[c] * sig[q][c]; }
     g += gdep * tmid[q] + gacc;
@@ -168,19 +176,32 @@ composite_bwd_kernel(const DurfCompositeArgs a, const float* __restrict__ d_comp
   // reverse exclusive scan of gw*w over samples
   float after = warp_rscan_excl(gwsum, lane);                    // sum over later lanes
   float gnorm = 0.f;
+  float od[kSPL], oc[kSPL * 3];                                    // this lane's 4 + 12 output floats (contiguous in both arrays)
 #pragma unroll
   for (int q = kSPL - 1; q >= 0; --q) {
     const bool ok = n0 + q < N;
     const float gs = gw[q] * trans[q] * (1.f - alpha[q]) - after;
     after += gw[q] * w[q];
-    if (ok) {
-      const float gdens = gs * (tdist[q] * dn);
-      d_raw_density[(size_t)ray * N + n0 + q] = a.activated ? gdens : gdens * sigmoidf(r.raw_d[q] + a.density_bias);
-      gnorm += gs * dens[q] * tdist[q];
+    const float gdens = gs * (tdist[q] * dn);
+    od[q] = a.activated ? gdens : gdens * sigmoidf(r.raw_d[q] + a.density_bias);
+    if (ok) gnorm += gs * dens[q] * tdist[q];
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        d_raw_rgb[((size_t)ray * N + n0 + q) * 3 + c] = a.activated ? gc[c] * w[q] : gc[c] * w[q] * sig[q][c] * (1.f - sig[q][c]);
-    }
+    for (int c = 0; c < 3; ++c) oc[3 * q + c] = a.activated ? gc[c] * w[q] : gc[c] * w[q] * sig[q][c] * (1.f - sig[q][c]);
+  }
+  if (N == 128) {      // whole 16-byte stores: 1 + 3 per lane instead of 16 strided 4-byte stores
+    *reinterpret_cast<float4*>(d_raw_density + (size_t)ray * N + n0) = make_float4(od[0], od[1], od[2], od[3]);
+    float4* o4 = reinterpret_cast<float4*>(d_raw_rgb + ((size_t)ray * N + n0) * 3);
+    o4[0] = make_float4(oc[0], oc[1], oc[2], oc[3]);
+    o4[1] = make_float4(oc[4], oc[5], oc[6], oc[7]);
+    o4[2] = make_float4(oc[8], oc[9], oc[10], oc[11]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < kSPL; ++q)
+      if (n0 + q < N) {
+        d_raw_density[(size_t)ray * N + n0 + q] = od[q];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d_raw_rgb[((size_t)ray * N + n0 + q) * 3 + c] = oc[3 * q + c];
+      }
   }
   if (d_dirs) {
     gnorm = warp_sum(gnorm);
