@@ -42,6 +42,9 @@ N_SAMPLES = 128
 MLP_FLOP_PER_SAMPLE = 1_183_744          # 591,872 MAC, background MLP forward
 BG_TOPO = (60, 256, 8, 4, 27, 128)
 CPU_SAMPLE_RAYS = 4096
+# both arms (ours / --impl reference) report the same workload string
+WORKLOAD_C2 = ("C2 full-frame render 1920x1280, background NeRF, mip360 contraction, hierarchical resampling, "
+               "2x128 samples")
 
 
 def load_peaks():
@@ -151,8 +154,9 @@ def run_reference(args, rank, world):
     line = dict(impl="reference", metric="rays/sec (render, 2x128 samples)", value=v, unit="rays/s", n_gpus=args.gpus, steps=steps,
                 warmup=args.warmup if args.warmup is not None else 1, ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="C2 full-frame render 1920x1280, background NeRF, mip360 contraction, 2x128 samples",
-                            rays_per_step=n, note="CPU restatement (oracle/durf_oracle.py) of the JAX reference; JAX is not installable here"),
+                config=dict(workload=WORKLOAD_C2, mlp="8x256 + cond 128, random init", rays_per_step=n,
+                            note="CPU restatement (oracle/durf_oracle.py) of the JAX reference on a bounded sample of the frame; "
+                                 "JAX is not installable here"),
                 cpu_baseline=dict(value=v, unit="rays/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=v, unit="rays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
@@ -446,8 +450,7 @@ def main():
     line = dict(metric="rays/sec (render, 2x128 samples)", value=value, unit="rays/s", n_gpus=world, steps=steps, warmup=warmup,
                 ms_per_step=ms_resident, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
-                config=dict(workload="C2 full-frame render 1920x1280, background NeRF, mip360 contraction, hierarchical resampling, "
-                                     "2x128 samples", rays_per_step_per_gpu=n_rays, chunk=chunk, mlp="8x256 + cond 128, random init",
+                config=dict(workload=WORKLOAD_C2, rays_per_step_per_gpu=n_rays, chunk=chunk, mlp="8x256 + cond 128, random init",
                             sharding="one camera frame per GPU, no collective",
                             l2="per-chunk working set (1 GB bf16 feature tiles) exceeds the 126 MB L2; no explicit flush"),
                 clocks=dict(sm_mhz=clocks["sm_mhz"], sm_max_mhz=clocks["sm_max_mhz"], reasons=clocks["reasons"],
