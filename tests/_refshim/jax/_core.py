@@ -102,23 +102,38 @@ class Array(torch.Tensor):
         out = out[0] if isinstance(out, tuple) else out
         return out.unsqueeze(axis) if keepdims else out
 
-    def sum(self, axis=None, dtype=None, keepdims=False):
+    def sum(self, axis=None, dtype=None, keepdims=False, out=None, **_):
         x = self
         if x.dtype == torch.bool:
             x = x.to(torch.int32)
         return x._red(lambda t, a: torch.sum(t, a), axis, keepdims)
 
-    def mean(self, axis=None, keepdims=False):
-        return self._red(lambda t, a: torch.mean(t, a), axis, keepdims)
+    def mean(self, axis=None, dtype=None, keepdims=False, out=None, **_):
+        x = self if self.dtype.is_floating_point else self.to(torch.float32)
+        return x._red(lambda t, a: torch.mean(t, a), axis, keepdims)
 
-    def prod(self, axis=None, keepdims=False):
+    def prod(self, axis=None, dtype=None, keepdims=False, out=None, **_):
         return self._red(lambda t, a: torch.prod(t, a), axis, keepdims)
 
-    def max(self, axis=None, keepdims=False):
+    def max(self, axis=None, keepdims=False, out=None, **_):
         return self._red(lambda t, a: torch.max(t, a), axis, keepdims)
 
-    def min(self, axis=None, keepdims=False):
+    def min(self, axis=None, keepdims=False, out=None, **_):
         return self._red(lambda t, a: torch.min(t, a), axis, keepdims)
+
+    def all(self, axis=None, keepdims=False, out=None, **_):
+        return self.to(torch.bool)._red(lambda t, a: torch.all(t, a), axis, keepdims)
+
+    def any(self, axis=None, keepdims=False, out=None, **_):
+        return self.to(torch.bool)._red(lambda t, a: torch.any(t, a), axis, keepdims)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kw):
+        """numpy ufuncs applied to (or mixed with) an Array compute in numpy and return numpy: `np.abs(a)`,
+        `ndarray += a`, `ndarray / a` in the reference's tests."""
+        conv = [_np.asarray(x) if isinstance(x, torch.Tensor) else x for x in inputs]
+        if out is not None:
+            kw['out'] = tuple(_np.asarray(o) if isinstance(o, torch.Tensor) else o for o in out)
+        return getattr(ufunc, method)(*conv, **kw)
 
     def astype(self, dt):
         return self.to(to_torch_dtype(dt))

@@ -12,21 +12,25 @@ pi = _math.pi
 inf = float('inf')
 nan = float('nan')
 newaxis = None
-float32 = _t.float32
-float64 = _t.float32
-float16 = _t.float16
-bfloat16 = _t.bfloat16
-int32 = _t.int32
-int64 = _t.int32
-uint8 = _t.uint8
-bool_ = _t.bool
-float_ = _t.float32
+# numpy scalar types: usable as dtype arguments of numpy AND of this module, and callable (`jnp.float32(x)`)
+float32 = _np.float32
+float64 = _np.float32
+float16 = _np.float16
+int32 = _np.int32
+int64 = _np.int32
+uint8 = _np.uint8
+bool_ = _np.bool_
+float_ = _np.float32
 
 
 def finfo(dt):
     if isinstance(dt, _t.dtype):
         dt = {_t.float32: 'float32', _t.float16: 'float16'}[dt]
     return _np.finfo(dt)
+
+
+def iinfo(dt):
+    return _np.iinfo(dt)
 
 
 def _w(x):
@@ -129,6 +133,23 @@ isnan = _unary(_t.isnan)
 isinf = _unary(_t.isinf)
 isfinite = _unary(_t.isfinite)
 floor = _unary(_t.floor)
+round = _unary(_t.round)
+arccos = _float_unary(_t.arccos)
+arcsin = _float_unary(_t.arcsin)
+log2 = _float_unary(_t.log2)
+log10 = _float_unary(_t.log10)
+
+
+def mod(a, b):
+    a, b = _pair(a, b)
+    return _w(_t.remainder(a, b))
+
+
+def histogram(x, bins):
+    """numpy semantics (right-most edge inclusive), computed in float64 numpy from the float32 values."""
+    h, e = _np.histogram(_np.asarray(asarray(x)), _np.asarray(asarray(bins)))
+    return asarray(h), asarray(e)
+
 square = _unary(lambda x: x * x)
 logical_not = _unary(_t.logical_not)
 
@@ -165,8 +186,10 @@ def clip(x, a_min=None, a_max=None):
     return x
 
 
-def where(c, a, b):
+def where(c, a=None, b=None):
     c = asarray(c)
+    if a is None and b is None:
+        return tuple(_w(i.to(_t.int32)) for i in _t.nonzero(c, as_tuple=True))
     a, b = _pair(a, b)
     if is_scalar(a) and is_scalar(b):
         a = asarray(a)
