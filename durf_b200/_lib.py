@@ -56,7 +56,7 @@ class RaymarchArgs(C.Structure):
                 ("origins", C.c_void_p), ("dirs", C.c_void_p), ("radii", C.c_void_p), ("near", C.c_void_p),
                 ("far", C.c_void_p), ("t_rand", C.c_void_p), ("t_vals", C.c_void_p), ("ray_mult", C.c_void_p),
                 ("ray_index", C.c_void_p), ("count", C.c_void_p), ("features", C.c_void_p), ("means", C.c_void_p),
-                ("cov_diag", C.c_void_p)]
+                ("cov_diag", C.c_void_p), ("alpha_dev", C.c_void_p)]
 
 
 class MlpArgs(C.Structure):
@@ -83,8 +83,19 @@ class LossArgs(C.Structure):
                 ("comp_rgb", C.c_void_p), ("depth", C.c_void_p), ("weights", C.c_void_p), ("t_vals", C.c_void_p),
                 ("pixels", C.c_void_p), ("depth_gt", C.c_void_p), ("sky", C.c_void_p), ("lossmult", C.c_void_p),
                 ("dyn_mask", C.c_void_p), ("zo", C.c_void_p), ("depth_mask", C.c_void_p), ("partials", C.c_void_p),
-                ("d_comp_rgb", C.c_void_p), ("d_depth", C.c_void_p), ("d_weights", C.c_void_p)]
+                ("d_comp_rgb", C.c_void_p), ("d_depth", C.c_void_p), ("d_weights", C.c_void_p),
+                ("reduce_ws", C.c_void_p), ("eps_dev", C.c_void_p)]
 
+
+class LossFinalizeArgs(C.Structure):
+    _fields_ = [("num_levels", C.c_int32), ("coarse_loss_mult", C.c_float), ("depth_loss_mult", C.c_float),
+                ("near_loss_mult", C.c_float), ("empty_loss_mult", C.c_float), ("sky_loss_mult", C.c_float),
+                ("tv_loss_mult", C.c_float), ("distortion_mult", C.c_float),
+                ("partials", C.c_void_p), ("norms", C.c_void_p), ("tv", C.c_void_p), ("weight_l2", C.c_void_p),
+                ("stats", C.c_void_p)]
+
+
+LS_STRIDE = 8
 
 # name -> (restype, argtypes); mirrors include/durf_b200.h one to one
 _vp, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -98,6 +109,8 @@ SIGNATURES = {
     "durf_generate_rays": (C.c_int, [_vp, C.POINTER(Camera), _i32, _i32] + [_vp] * 7),
     "durf_aa2matrix_fwd": (C.c_int, [_vp, _i32, _vp, _vp]),
     "durf_obb_frontend_fwd": (C.c_int, [_vp, _i32, _i32] + [_vp] * 13),
+    "durf_world2object_fwd": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
+    "durf_ray_box_intersection_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "durf_obb_frontend_bwd": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "durf_compact_hits": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "durf_raymarch_fwd": (C.c_int, [_vp, C.POINTER(RaymarchArgs)]),
@@ -116,6 +129,9 @@ SIGNATURES = {
     "durf_losses_fwd_bwd": (C.c_int, [_vp, C.POINTER(LossArgs), _vp]),
     "durf_grad_sanitize": (C.c_int, [_vp, _i64, _vp, _f, _f, _vp]),
     "durf_adam_step": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f, _f, C.c_double, C.c_double, C.c_double, _i32]),
+    "durf_adam_step_dev": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i32, C.c_double, C.c_double, C.c_double]),
+    "durf_losses_reduce_ws_floats": (_i64, [_i32]),
+    "durf_losses_finalize": (C.c_int, [_vp, C.POINTER(LossFinalizeArgs)]),
 }
 
 _lib: Optional[C.CDLL] = None

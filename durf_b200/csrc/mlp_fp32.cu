@@ -65,7 +65,7 @@ gemm_nn_kernel(int M, int Nn, RowSrc A, const float* __restrict__ W, int ldw, co
       const int n = n0 + tx * 4 + j;
       if (n >= Nn) continue;
       float v = acc[i][j] + bias[n];
-      if (RELU) v = fmaxf(v, 0.f);
+      if (RELU) v = (v < 0.f) ? 0.f : v;          // jnp.maximum(x, 0) propagates NaN (fmaxf would return 0)
       C[(size_t)m * ldc + n] = v;
     }
   }

@@ -126,6 +126,60 @@ obb_frontend_kernel(int B, int K, const float* __restrict__ origins, const float
   nhit[b] = (float)hsum;
 }
 
+// box_helpers.world2object_rpy(pts, dirs, pose, rot) with EXPLICIT rotation matrices (box_helpers.py:286-341, dim=None,
+// inverse=False): o_o = R o + R (-p), d_o = R d / |R d|.  pose / rot may be per object ([K,..], stride 0 over rays) or
+// per ray and object ([B,K,..]).  One thread per (ray, object).
+__global__ void __launch_bounds__(256)
+world2object_kernel(int B, int K, const float* __restrict__ pts, const float* __restrict__ dirs,
+                    const float* __restrict__ pose, int64_t pose_stride, const float* __restrict__ rot, int64_t rot_stride,
+                    float* __restrict__ pts_o, float* __restrict__ dirs_o) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * K) return;
+  const int b = (int)(i / K), k = (int)(i % K);
+  const float* R = rot + (int64_t)b * rot_stride + 9 * k;
+  const float* p = pose + (int64_t)b * pose_stride + 3 * k;
+  const float o[3] = {pts[3 * b], pts[3 * b + 1], pts[3 * b + 2]};
+  const float d[3] = {dirs[3 * b], dirs[3 * b + 1], dirs[3 * b + 2]};
+  float oo[3], dd[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float t = R[3 * r] * (-p[0]) + R[3 * r + 1] * (-p[1]) + R[3 * r + 2] * (-p[2]);     // rotate_matrix(-pose_w, rot)
+    oo[r] = (R[3 * r] * o[0] + R[3 * r + 1] * o[1] + R[3 * r + 2] * o[2]) + t;
+    dd[r] = R[3 * r] * d[0] + R[3 * r + 1] * d[1] + R[3 * r + 2] * d[2];
+  }
+  const float nrm = sqrtf(dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    pts_o[3 * i + r] = oo[r];
+    dirs_o[3 * i + r] = dd[r] / nrm;
+  }
+}
+
+// box_helpers.ray_box_intersection (box_helpers.py:59-106) on n = B*K (ray, box) pairs: slab test, NaN-propagating
+// min / max like jnp, intersection = (t_far > t_near) * (t_far * intersection > 0).
+__global__ void __launch_bounds__(256)
+ray_box_kernel(int64_t n, const float* __restrict__ ray_o, const float* __restrict__ ray_d, const float* __restrict__ bmin,
+               const float* __restrict__ bmax, float* __restrict__ zi, float* __restrict__ zo, int32_t* __restrict__ hit) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float tn = 0.f, tf = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float inv = 1.f / ray_d[3 * i + c];
+    const float o = ray_o[3 * i + c];
+    const float tmin = ((bmin ? bmin[3 * i + c] : -1.f) - o) * inv;
+    const float tmax = ((bmax ? bmax[3 * i + c] : 1.f) - o) * inv;
+    const float t0 = nmin(tmin, tmax), t1 = nmax(tmin, tmax);
+    tn = (c == 0) ? t0 : nmax(tn, t0);
+    tf = (c == 0) ? t1 : nmin(tf, t1);
+  }
+  int h = (tf > tn) ? 1 : 0;
+  h *= ((tf * (float)h) > 0.f) ? 1 : 0;
+  hit[i] = h;
+  zi[i] = tn * (float)h;
+  zo[i] = tf * (float)h;
+}
+
 // Warp-aggregated compaction of the rays with hit[:,k] != 0 (unordered: results are scattered back per ray).
 __global__ void compact_hits_kernel(int B, int K, int k, const int32_t* __restrict__ hit,
                                     int32_t* __restrict__ ray_index, int32_t* __restrict__ count) {
@@ -241,6 +295,29 @@ extern "C" int durf_aa2matrix_fwd(durf_stream_t stream, int32_t K, const float* 
   if (K == 0) return DURF_OK;
   aa2matrix_kernel<<<ceil_div(K, 64), 64, 0, (cudaStream_t)stream>>>(K, angles, R);
   DURF_CHECK_LAUNCH("durf_aa2matrix_fwd");
+  return DURF_OK;
+}
+
+extern "C" int durf_world2object_fwd(durf_stream_t stream, int32_t B, int32_t K, const float* pts, const float* dirs,
+                                     const float* pose, int32_t pose_per_ray, const float* rot, int32_t rot_per_ray,
+                                     float* pts_o, float* dirs_o) {
+  DURF_REQUIRE(B >= 0 && K >= 1, DURF_E_INVALID, "durf_world2object_fwd: bad shape B=%d K=%d", B, K);
+  if (B == 0) return DURF_OK;
+  DURF_REQUIRE(pts && dirs && pose && rot && pts_o && dirs_o, DURF_E_INVALID, "durf_world2object_fwd: null argument");
+  world2object_kernel<<<ceil_div((int64_t)B * K, 256), 256, 0, (cudaStream_t)stream>>>(
+      B, K, pts, dirs, pose, pose_per_ray ? (int64_t)K * 3 : 0, rot, rot_per_ray ? (int64_t)K * 9 : 0, pts_o, dirs_o);
+  DURF_CHECK_LAUNCH("durf_world2object_fwd");
+  return DURF_OK;
+}
+
+extern "C" int durf_ray_box_intersection_fwd(durf_stream_t stream, int64_t n, const float* ray_o, const float* ray_d,
+                                             const float* aabb_min, const float* aabb_max, float* z_in, float* z_out,
+                                             int32_t* intersection) {
+  DURF_REQUIRE(n >= 0, DURF_E_INVALID, "durf_ray_box_intersection_fwd: negative size");
+  if (n == 0) return DURF_OK;
+  DURF_REQUIRE(ray_o && ray_d && z_in && z_out && intersection, DURF_E_INVALID, "durf_ray_box_intersection_fwd: null argument");
+  ray_box_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(n, ray_o, ray_d, aabb_min, aabb_max, z_in, z_out, intersection);
+  DURF_CHECK_LAUNCH("durf_ray_box_intersection_fwd");
   return DURF_OK;
 }
 

@@ -197,7 +197,7 @@ raymarch_fwd_kernel(const RayMarchParams p) {
   const bool weighted = (a.flags & DURF_RM_WEIGHTED) != 0;
   if (threadIdx.x < 16) {
     // mip.py:217-218: w_k = (1 - cos(clip(alpha - k, 0, 1) * pi)) / 2
-    const float c = fminf(fmaxf(a.alpha - (float)threadIdx.x, 0.f), 1.f);
+    const float c = fminf(fmaxf((a.alpha_dev ? *a.alpha_dev : a.alpha) - (float)threadIdx.x, 0.f), 1.f);
     s_w[threadIdx.x] = (1.f - cosf(c * 3.14159265358979324f)) / 2.f;
   }
   __syncthreads();
@@ -274,7 +274,7 @@ raymarch_bwd_kernel(const RayMarchParams p, const float* __restrict__ d_features
   float* s_w = smem;
   float* s_t = smem + 16 + warp * (7 * N + 1);
   if (threadIdx.x < 16) {
-    const float c = fminf(fmaxf(a.alpha - (float)threadIdx.x, 0.f), 1.f);
+    const float c = fminf(fmaxf((a.alpha_dev ? *a.alpha_dev : a.alpha) - (float)threadIdx.x, 0.f), 1.f);
     s_w[threadIdx.x] = (1.f - cosf(c * 3.14159265358979324f)) / 2.f;
   }
   __syncthreads();

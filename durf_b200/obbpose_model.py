@@ -58,6 +58,10 @@ class MipNerfModel:
     net_width_condition: int = 128
     # which MLP kernels to use: 'bf16' = tcgen05 chain (throughput), 'fp32' = CUDA-core parity mode
     precision: str = 'bf16'
+    # Rows reserved per object for the compacted hit-ray buffers of the tensor-core path (None = the whole batch).  The
+    # hit COUNT stays on the device (no host sync); lower this to save memory when few rays hit a box -- rays beyond the
+    # cap would be dropped, so `apply` records the overflow in ctx['obj_overflow'] (a device flag) for the caller to check.
+    max_obj_rays: Optional[int] = None
 
     # -- topology helpers ------------------------------------------------------------------------------
     def bg_topology(self):
@@ -93,6 +97,13 @@ class MipNerfModel:
         """MipNerfModel.__call__ (obbpose_model.py:69-261).  `init` is accepted for signature parity (the box
         parameters live in `variables`, as `self.param('box_centers', ...)` does after initialisation).
         When `ctx` (a dict) is given the forward keeps what the backward pass needs in it."""
+        if self.lindisp:
+            # the reference's lindisp branch (mip.py:354-356) is never enabled by the shipped gin files; refuse rather
+            # than silently sample linearly in depth
+            raise NotImplementedError("lindisp=True is not implemented (configs/*.gin set MipNerfModel.lindisp = False)")
+        if not self.stop_level_grad and ctx is not None:
+            raise NotImplementedError("stop_level_grad=False: the backward pass treats resampled t_vals as constants "
+                                      "(mip.py:413-414 with the reference's default stop_level_grad=True)")
         prec = L.PREC_BF16 if self.precision == 'bf16' else L.PREC_FP32
         # Joint box-pose optimisation needs the gradient w.r.t. the object MLPs' input features.  The tensor-core backward
         # produces it for width-128 networks (the BoxMLP default); other widths fall to the fp32 kernels for the objects.
@@ -102,8 +113,17 @@ class MipNerfModel:
         origins, dirs = ops.f32(rays.origins), ops.f32(rays.directions)
         B = origins.shape[0]
         dev = origins.device
-        ts_i = int(ts.reshape(-1)[0].item()) if torch.is_tensor(ts) else int(np.asarray(ts).reshape(-1)[0])
-        box = variables.box_centers[ts_i].contiguous()                       # [K,6]
+        if torch.is_tensor(ts) and ts.is_cuda:
+            # device-resident timestep (captured CUDA graphs): gather the row on the device, no host read
+            ts_i = ts.reshape(-1)[:1].long()
+            box = variables.box_centers.index_select(0, ts_i)[0].contiguous()
+        else:
+            ts_h = ts.reshape(-1) if torch.is_tensor(ts) else torch.as_tensor(np.asarray(ts)).reshape(-1)
+            # the reference indexes pose_offsets[ts.squeeze()] (obbpose_model.py:99): one timestep per batch
+            # ('timestep' batching); a batch mixing timesteps would silently use the wrong boxes
+            assert bool((ts_h == ts_h[0]).all()), "all rays of a batch must share one timestep (Config.batching = 'timestep')"
+            ts_i = int(ts_h[0])
+            box = variables.box_centers[ts_i].contiguous()                   # [K,6]
         K = box.shape[0]
         ext = ops.f32(torch.as_tensor(ext, device=dev)).reshape(K, 3)
         rb = _rand_buffers(rng, randomized, B, N, self.num_levels, self.density_noise, dev)
@@ -117,11 +137,15 @@ class MipNerfModel:
         bg_mult = None
         if self.dynamics:
             bg_mult = 1.0 - fe['nhit']                                       # 1 - sum_k mask_k (obbpose_model.py:205)
+            cap = B if self.max_obj_rays is None else min(B, self.max_obj_rays)
+            overflow = torch.zeros((), device=dev, dtype=torch.bool) if cap < B else None
             for k in range(K):
                 idx, cnt = ops.compact_hits(hit, k)
+                if overflow is not None:
+                    overflow = overflow | (cnt[0] > cap)
                 m_host = None
-                if obj_prec == L.PREC_FP32 or ctx is not None:
-                    m_host = int(cnt.item())                                 # parity / training size their buffers exactly
+                if obj_prec == L.PREC_FP32:
+                    m_host = int(cnt.item())                                 # the fp32 parity GEMMs are sized on the host
                 obj_lists.append((idx, cnt, m_host))
         bt, ot = self.bg_topology(), self.box_topology()
         bf16 = prec == L.PREC_BF16
@@ -131,7 +155,8 @@ class MipNerfModel:
         ret = []
         t_vals = weights = None
         if ctx is not None:
-            ctx.update(dict(fe=fe, viewenc=viewenc, obj_lists=obj_lists, levels=[], B=B, K=K, ts=ts_i, alpha=alpha, obj_prec=obj_prec,
+            ctx.update(dict(fe=fe, viewenc=viewenc, obj_lists=obj_lists, levels=[], B=B, K=K, ts=ts_i,
+                            obj_overflow=overflow if self.dynamics else None, alpha=alpha, obj_prec=obj_prec,
                             white_bkgd=white_bkgd, rand_bkgd=rand_bkgd, rays=rays, box=box, radii=radii))
         for i_level in range(self.num_levels):
             common = dict(min_deg=self.min_deg_point, max_deg=self.max_deg_point, ray_shape=self.ray_shape,
@@ -154,7 +179,7 @@ class MipNerfModel:
                         if lvl_ctx is not None:
                             lvl_ctx['obj'].append(None)
                         continue
-                    rows = m_host if m_host is not None else B
+                    rows = m_host if m_host is not None else (B if self.max_obj_rays is None else min(B, self.max_obj_rays))
                     rmo = ops.raymarch(origins_s, dirs_s, radii, N, t_vals=t_vals, weighted=True, alpha=alpha, ray_index=idx,
                                        count=None if m_host is not None else cnt, rows=rows,
                                        **dict(common, bf16_tiles=obj_prec == L.PREC_BF16))
@@ -172,17 +197,21 @@ class MipNerfModel:
             weights = comp['weights']
             dyn_mask = fe['nhit'].reshape(B, 1)
             ret.append((comp['comp_rgb'], comp['depth'], comp['acc'], weights, t_vals, comp['t_mids'], comp['t_dists'],
-                        [box[:, :3], box[:, 3:]], dyn_mask, fe['zo_ret']))
+                        [box[:, :3], box[0, 3:]], dyn_mask, fe['zo_ret']))   # [box_pose[0], box_rot[0]] (obbpose_model.py:258): [K,3], [3]
             if lvl_ctx is not None:
                 lvl_ctx.update(raw_rgb=raw_rgb, raw_density=raw_density, t_vals=t_vals)
                 ctx['levels'].append(lvl_ctx)
         return ret
 
     # -- backward ----------------------------------------------------------------------------------------
-    def backward(self, variables: "Variables", ctx: dict, level_grads: Sequence[dict], d_flat: torch.Tensor) -> None:
+    def backward(self, variables: "Variables", ctx: dict, level_grads: Sequence[dict], d_flat: torch.Tensor,
+                 on_network_done=None) -> None:
         """Reverse of `apply` (what jax.value_and_grad does through model.apply, train_boxpose.py:251): given per level
         dL/d(comp_rgb, depth, weights) accumulate dL/d parameters into `d_flat` (same layout as variables.flat).
-        Levels are independent: t_vals are stop_gradient'ed (mip.py:413-414)."""
+        Levels are independent: t_vals are stop_gradient'ed (mip.py:413-414).
+
+        Order: background MLP (both levels), then each object MLP, then the box parameters; `on_network_done(name)` is
+        called as soon as a network's slice of d_flat is final, so its all-reduce overlaps the rest of the backward."""
         N = self.num_samples
         fe, viewenc = ctx['fe'], ctx['viewenc']
         B, K = ctx['B'], ctx['K']
@@ -190,17 +219,23 @@ class MipNerfModel:
         pose_opt = self.dynamics and not (self.no_pose_opt and self.no_yaw_opt)
         d_os = torch.zeros(B, 3, device=d_flat.device) if pose_opt else None
         d_ds = torch.zeros(B, 3, device=d_flat.device) if pose_opt else None
+        done = on_network_done or (lambda name: None)
+        prec = L.PREC_BF16 if self.precision == 'bf16' else L.PREC_FP32
+        raw_grads = []
         for lvl, g in zip(ctx['levels'], level_grads):
             g_rgb, g_den, g_dirs = ops.composite_bwd(lvl['raw_rgb'], lvl['raw_density'], lvl['t_vals'], fe['dirs_s'],
                                                      g['comp_rgb'], g['depth'], g['weights'], white_bkgd=ctx['white_bkgd'],
                                                      rand_bkgd=ctx['rand_bkgd'], density_bias=self.density_bias,
                                                      want_d_dirs=pose_opt)
-            prec = L.PREC_BF16 if self.precision == 'bf16' else L.PREC_FP32
-            ops.mlp_bwd(bt, lvl['feat_bg'], viewenc, variables.blob('MLP_0'), lvl['saved_bg'], g_rgb, g_den,
-                        variables.blob_of(d_flat, 'MLP_0'), M=B, N=N, precision=prec, packed=variables.packed.get('MLP_0'))
+            raw_grads.append((g_rgb, g_den))
             if pose_opt:
                 d_ds += g_dirs * (fe['nhit'] > 0).float()[:, None]            # only object rays carry pose-dependent dirs
-            for k, o in enumerate(lvl['obj']):
+            ops.mlp_bwd(bt, lvl['feat_bg'], viewenc, variables.blob('MLP_0'), lvl['saved_bg'], g_rgb, g_den,
+                        variables.blob_of(d_flat, 'MLP_0'), M=B, N=N, precision=prec, packed=variables.packed.get('MLP_0'))
+        done('MLP_0')
+        for k in range(K if self.dynamics else 0):
+            for lvl, (g_rgb, g_den) in zip(ctx['levels'], raw_grads):
+                o = lvl['obj'][k]
                 if o is None:
                     continue
                 idx = ctx['obj_lists'][k][0]
@@ -213,14 +248,22 @@ class MipNerfModel:
                     gd = torch.zeros(B, 3, device=d_flat.device)
                     ops.raymarch_bwd(fe['origins_s'], fe['dirs_s'], ctx['radii'], lvl['t_vals'], dfeat, weighted=True,
                                      alpha=ctx['alpha'], min_deg=self.min_deg_point, max_deg=self.max_deg_point, ray_index=idx,
-                                     rows=o['rows'], d_origins=go, d_dirs=gd)
+                                     rows=o['rows'], count=o.get('count'), d_origins=go, d_dirs=gd)
                     d_os += go
                     d_ds += gd
+            done(f'BoxMLP_{k}')
+        for k in range(0 if self.dynamics else K):
+            done(f'BoxMLP_{k}')                                              # static scene: object networks get no gradient
         if pose_opt:
             d_box = torch.zeros(K, 6, device=d_flat.device)
             ops.obb_frontend_bwd(ctx['rays'].origins, ctx['rays'].directions, ctx['box'], fe['hit'], d_os, d_ds,
                                  pose_grad=not self.no_pose_opt, rot_grad=not self.no_yaw_opt, d_box=d_box)
-            variables.view_of(d_flat, 'box_centers')[ctx['ts']] += d_box
+            bc = variables.view_of(d_flat, 'box_centers')
+            if torch.is_tensor(ctx['ts']):
+                bc.index_add_(0, ctx['ts'], d_box[None])
+            else:
+                bc[ctx['ts']] += d_box
+        done('box_centers')
 
 
 def _rand_buffers(rng, randomized: bool, B: int, N: int, levels: int, density_noise: float, dev) -> dict:

@@ -139,10 +139,11 @@ def raymarch(origins, dirs, radii, N: int, *, t_vals=None, near=None, far=None, 
         feats = torch.empty(M, N, F, device=dev)
     means = torch.empty(M, N, 3, device=dev) if want_gaussians else None
     covd = torch.empty(M, N, 3, device=dev) if want_gaussians else None
-    a = L.RaymarchArgs(B=M, N=N, min_deg=min_deg, max_deg=max_deg, flags=flags, alpha=float(alpha),
+    alpha_dev = alpha if torch.is_tensor(alpha) else None          # device scalar: a captured graph follows alpha_rate_fn
+    a = L.RaymarchArgs(B=M, N=N, min_deg=min_deg, max_deg=max_deg, flags=flags, alpha=0.0 if alpha_dev is not None else float(alpha),
                        origins=ptr(origins), dirs=ptr(dirs), radii=ptr(radii), near=ptr(near), far=ptr(far),
                        t_rand=ptr(t_rand), t_vals=ptr(t_vals), ray_mult=ptr(ray_mult), ray_index=ptr(ray_index),
-                       count=ptr(count), features=ptr(feats), means=ptr(means), cov_diag=ptr(covd))
+                       count=ptr(count), features=ptr(feats), means=ptr(means), cov_diag=ptr(covd), alpha_dev=ptr(alpha_dev))
     check(L.load().durf_raymarch_fwd(stream_ptr(), C.byref(a)), "durf_raymarch_fwd")
     out = dict(t_vals=t_vals, features=feats)
     if want_gaussians:
@@ -151,16 +152,17 @@ def raymarch(origins, dirs, radii, N: int, *, t_vals=None, near=None, far=None, 
 
 
 def raymarch_bwd(origins, dirs, radii, t_vals, d_features, *, weighted, alpha, min_deg=0, max_deg=10, ray_mult=None,
-                 ray_index=None, rows=None, d_origins=None, d_dirs=None):
+                 ray_index=None, rows=None, count=None, d_origins=None, d_dirs=None):
     """Gradient of the object-frame encoding w.r.t. origins_s / dirs_s (written for the rays in ray_index)."""
     B = origins.shape[0]
     N = t_vals.shape[1] - 1
     M = B if rows is None else rows
     flags = L.RM_WEIGHTED if weighted else 0
-    a = L.RaymarchArgs(B=M, N=N, min_deg=min_deg, max_deg=max_deg, flags=flags, alpha=float(alpha),
+    alpha_dev = alpha if torch.is_tensor(alpha) else None
+    a = L.RaymarchArgs(B=M, N=N, min_deg=min_deg, max_deg=max_deg, flags=flags, alpha=0.0 if alpha_dev is not None else float(alpha),
                        origins=ptr(f32(origins)), dirs=ptr(f32(dirs)), radii=ptr(f32(radii).reshape(-1)), near=None, far=None,
-                       t_rand=None, t_vals=ptr(f32(t_vals)), ray_mult=ptr(ray_mult), ray_index=ptr(ray_index), count=None,
-                       features=ptr(d_features), means=None, cov_diag=None)
+                       t_rand=None, t_vals=ptr(f32(t_vals)), ray_mult=ptr(ray_mult), ray_index=ptr(ray_index), count=ptr(count),
+                       features=ptr(d_features), means=None, cov_diag=None, alpha_dev=ptr(alpha_dev))
     check(L.load().durf_raymarch_bwd(stream_ptr(), C.byref(a), ptr(f32(d_features)), ptr(d_origins), ptr(d_dirs)),
           "durf_raymarch_bwd")
 
@@ -316,10 +318,17 @@ def resample(t_vals, weights, *, u_rand=None, padding=0.01, blurpool=True, num_s
 
 
 # ---- KL / KA ----------------------------------------------------------------------------------------
-def loss_args(level, num_levels, eps, cfg, lv, batch, depth_mask, partials, grads):
+def losses_reduce_ws(B: int, device) -> torch.Tensor:
+    """Zero-initialised workspace of the deterministic loss reduction (allocate once, reuse every step)."""
+    return torch.zeros(int(L.load().durf_losses_reduce_ws_floats(B)), device=device)
+
+
+def loss_args(level, num_levels, eps, cfg, lv, batch, depth_mask, partials, grads, reduce_ws):
     B, N = lv['weights'].shape
     g = grads
-    return L.LossArgs(B=B, N=N, level=level, num_levels=num_levels, eps=float(eps),
+    eps_dev = eps if torch.is_tensor(eps) else None
+    return L.LossArgs(B=B, N=N, level=level, num_levels=num_levels, eps=0.0 if eps_dev is not None else float(eps),
+                      reduce_ws=ptr(reduce_ws), eps_dev=ptr(eps_dev),
                       coarse_loss_mult=cfg.coarse_loss_mult, box_loss_mult=cfg.box_loss_mult,
                       depth_loss_mult=cfg.depth_loss_mult, near_loss_mult=cfg.near_loss_mult,
                       empty_loss_mult=cfg.empty_loss_mult, sky_loss_mult=cfg.sky_loss_mult, distortion_mult=1e-6,
@@ -343,6 +352,13 @@ def grad_sanitize(grad: torch.Tensor, max_val: float, scale: float, sumsq: torch
           "durf_grad_sanitize")
 
 
-def adam_step(params, grad, m, v, sumsq, *, max_norm, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+def adam_step(params, grad, m, v, sumsq, *, max_norm, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, advance_step=True):
+    """flax.optim.Adam.  `lr` / `step` are Python numbers, or device tensors (float32[1] / int32[1]) for a captured graph;
+    in the device form the kernel increments the step counter itself when advance_step."""
+    if torch.is_tensor(lr) or torch.is_tensor(step):
+        check(L.load().durf_adam_step_dev(stream_ptr(), params.numel(), ptr(params), ptr(grad), ptr(m), ptr(v), ptr(sumsq),
+                                          float(max_norm), ptr(lr), ptr(step), int(advance_step), beta1, beta2, eps),
+              "durf_adam_step_dev")
+        return
     check(L.load().durf_adam_step(stream_ptr(), params.numel(), ptr(params), ptr(grad), ptr(m), ptr(v), ptr(sumsq),
                                   float(max_norm), float(lr), beta1, beta2, eps, int(step)), "durf_adam_step")

@@ -46,6 +46,46 @@ def allreduce_gradients(d_flat: torch.Tensor) -> float:
     return 1.0 / w
 
 
+class GradientBuckets:
+    """The gradient mean of the train step (jax.lax.pmean(grad, 'batch'), train_boxpose.py:253) as one SUM all-reduce per
+    network, launched on a side stream as soon as that network's slice of the flat gradient is final, so it overlaps the
+    rest of the backward pass; `finish()` joins the side stream and returns the 1/world factor (folded into
+    durf_grad_sanitize).  The buckets are the contiguous slices of `Variables.flat`: MLP_0 | BoxMLP_k | box_centers."""
+
+    _streams = {}
+
+    def __init__(self, variables, d_flat: torch.Tensor, world: int):
+        self.v, self.d_flat, self.world = variables, d_flat, world
+        self.works = []
+        self.cuda = d_flat.is_cuda
+        if self.cuda:
+            key = d_flat.device.index
+            if key not in GradientBuckets._streams:
+                GradientBuckets._streams[key] = torch.cuda.Stream(device=d_flat.device)
+            self.side = GradientBuckets._streams[key]
+
+    def network_done(self, name: str) -> None:
+        if self.world <= 1:
+            return
+        bucket = self.v.blob_of(self.d_flat, name)
+        if not self.cuda:
+            dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
+            return
+        ev = torch.cuda.Event()
+        ev.record()                                   # everything enqueued so far on the compute stream
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            self.works.append(dist.all_reduce(bucket, op=dist.ReduceOp.SUM, async_op=True))
+
+    def finish(self) -> float:
+        for w in self.works:
+            w.wait()                                  # the compute stream waits for the collective, the host does not
+        if self.cuda and self.works:
+            torch.cuda.current_stream().wait_stream(self.side)
+        self.works = []
+        return 1.0 / self.world
+
+
 def max_over_ranks(value: float, device) -> float:
     """Timing rule: a multi-GPU number is the MAX over ranks of the device-side time."""
     if world_size() == 1:

@@ -27,11 +27,16 @@ from .utils import Config, Rays, load_gin
 class SyntheticTimestepDataset:
     """Batches shaped like `Carla._next_train` with batching='timestep' (obbpose_dataset.py:293-328), synthetic content."""
 
-    def __init__(self, config: Config, num_objects: int, device, seed: int = S.SEED):
+    def __init__(self, config: Config, num_objects: int, device, seed: int = S.SEED, rank: int = 0):
         self.cfg, self.K, self.dev = config, num_objects, device
-        self.rng = np.random.default_rng(seed)
-        self.c2w = [S.random_c2w(self.rng) for _ in range(config.timesteps)]
-        self.centers, self.ext = S.boxes_in_view(self.rng, self.c2w[0], num_objects, timesteps=config.timesteps)
+        # The SCENE (cameras, boxes, hence the initial box_centers parameter) is the same on every rank: the reference
+        # replicates one state to all devices (flax.jax_utils.replicate, train_boxpose.py:407) and shards only the batch.
+        scene_rng = np.random.default_rng(seed)
+        self.c2w = [S.random_c2w(scene_rng) for _ in range(config.timesteps)]
+        self.centers, self.ext = S.boxes_in_view(scene_rng, self.c2w[0], num_objects, timesteps=config.timesteps)
+        # the per-rank stream only draws pixels / targets; the timestep sequence is shared (one `ts` per global batch)
+        self.ts_rng = np.random.default_rng(seed + 7919)
+        self.rng = np.random.default_rng(seed + 104729 * (rank + 1))
 
     def peek(self) -> Dict:
         return dict(init=self.centers, ext=self.ext)
@@ -39,7 +44,7 @@ class SyntheticTimestepDataset:
     def __iter__(self) -> Iterator[Dict]:
         B = self.cfg.batch_size
         while True:
-            ts = int(self.rng.integers(0, self.cfg.timesteps))
+            ts = int(self.ts_rng.integers(0, self.cfg.timesteps))
             rays, _ = S.random_rays(self.rng, B, c2w=self.c2w[ts], near=self.cfg.near, far=self.cfg.far)
             tg = S.targets(self.rng, B)
             to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev, non_blocking=True)
@@ -73,9 +78,13 @@ def main(argv=None) -> Dict:
     config = Config(**cfg_kw)
     model = MipNerfModel(precision=args.precision, timesteps=config.timesteps,
                          **{k: v for k, v in model_kw.items() if k in MipNerfModel.__dataclass_fields__})
-    dataset = SyntheticTimestepDataset(config, model.num_objects, dev, seed=S.SEED + rank)
+    dataset = SyntheticTimestepDataset(config, model.num_objects, dev, seed=S.SEED, rank=rank)
     variables = model.init(np.random.default_rng(20200823), dataset.peek()["init"], device=dev)       # train_boxpose.py:325
     state = checkpoint.restore_checkpoint(args.train_dir, TrainState.create(variables))
+    if world > 1:
+        # replicas must start from identical parameters and moments whatever was restored on each rank
+        for t in (variables.flat, state.m, state.v):
+            torch.distributed.broadcast(t, 0)
     init_step = state.step + 1 if state.step > 0 else 1
     lr_fn = lambda s: dmath.learning_rate_decay(s, config.lr_init, config.lr_final, config.max_steps, config.lr_delay_steps,
                                                 config.lr_delay_mult)
@@ -87,10 +96,10 @@ def main(argv=None) -> Dict:
     t0, losses, last = time.time(), [], {}
     for step, batch in zip(range(init_step, config.max_steps + 1), dataset):
         ts = batch["ts"]
-        prev = prevs[ts + 1 if ts == 0 else ts - 1, :, :3]
+        prev = prevs[ts + 1 if ts == 0 else ts - 1][None]                        # train_boxpose.py:453-456
         state, stats = train_step(model, config, None, state, batch, lr_fn(step), eps_fn(step), alpha_fn(step), prev=prev,
                                   world_size=world)
-        prevs[ts, :, :3] = variables.box_centers[ts, :, :3]
+        prevs[ts, :, :3] = stats['pose']              # the FORWARD pass's pose (stats.pose), not the post-Adam one (:461)
         state.step = step
         if step % args.print_every == 0 or step == config.max_steps:
             torch.cuda.synchronize()

@@ -68,6 +68,19 @@ int64_t durf_mlp_param_offset(const DurfMlpTopology* topo, int32_t layer, int32_
 /* box_helpers.aa2matrix (box_helpers.py:148-167): angles [K,3] -> R [K,3,3]. */
 int durf_aa2matrix_fwd(durf_stream_t stream, int32_t K, const float* angles, float* R);
 
+/* box_helpers.world2object_rpy(pts, dirs, pose, rot) (box_helpers.py:286-341; dim=None, inverse=False) with explicit
+ * rotation matrices: pts, dirs [B,3]; pose [K,3] or [B,K,3] (pose_per_ray); rot [K,3,3] or [B,K,3,3] (rot_per_ray)
+ * -> pts_o, dirs_o [B,K,3] (dirs_o unit length, box_helpers.py:340). */
+int durf_world2object_fwd(durf_stream_t stream, int32_t B, int32_t K, const float* pts, const float* dirs,
+                          const float* pose, int32_t pose_per_ray, const float* rot, int32_t rot_per_ray,
+                          float* pts_o, float* dirs_o);
+
+/* box_helpers.ray_box_intersection(ray_o, ray_d, aabb_min, aabb_max) (box_helpers.py:59-106) on n (ray, box) pairs:
+ * ray_o, ray_d, aabb_min, aabb_max [n,3] (NULL bounds = the unit box) -> z_in, z_out [n], intersection [n] int32. */
+int durf_ray_box_intersection_fwd(durf_stream_t stream, int64_t n, const float* ray_o, const float* ray_d,
+                                  const float* aabb_min, const float* aabb_max, float* z_in, float* z_out,
+                                  int32_t* intersection);
+
 /* box_helpers.world2object_rpy (box_helpers.py:286-341) + ray_box_intersection (:59-106) +
  * the scene-graph merge of MipNerfModel.__call__ (obbpose_model.py:99-131).
  *   origins, directions [B,3]; box [K,6] = box_centers[ts] (xyz + axis-angle); ext [K,3] half-extents.
@@ -138,6 +151,7 @@ typedef struct DurfRaymarchArgs {
   void* features;       /* fp32 [M,N,F] (F = 60 or 63)  or  bf16 tile images [M*N/128][128x64] */
   float* means;         /* [opt] [M,N,3] cast_rays means (after ray_mult / contraction), parity tests */
   float* cov_diag;      /* [opt] [M,N,3] covariance diagonal fed to the encoding */
+  const float* alpha_dev;  /* [opt] device scalar overriding `alpha` (lets a captured CUDA graph follow alpha_rate_fn) */
 } DurfRaymarchArgs;
 
 /* mip.sample_along_rays / cast_rays / mip360.new_space / integrated_pos_enc / weighted_ipe
@@ -247,10 +261,14 @@ typedef struct DurfLossArgs {
   const float* dyn_mask;       /* [B] nhit */
   const float* zo;             /* [B] zo_ret */
   float* depth_mask;           /* [B] in/out: accumulates across levels (train_boxpose.py:140); level 0 initialises it */
-  float* partials;             /* [16] fp32 accumulators (caller zeroes before level 0 of a step) -- see DURF_LP_* */
+  float* partials;             /* [num_levels * 8] sums of the level are WRITTEN (not accumulated) -- see DURF_LP_* */
   float* d_comp_rgb;           /* [B,3] gradient of the total loss */
   float* d_depth;              /* [B] */
-  float* d_weights;            /* [B,N] */
+  float* d_weights;            /* [B,N]; 16-byte aligned rows use vector stores, otherwise scalar stores */
+  float* reduce_ws;            /* durf_losses_reduce_ws_floats(B) floats, zero-initialised ONCE by the caller: per-block partial
+                                  sums + a ticket; the last block adds them in a fixed order (deterministic loss value) and
+                                  re-arms the ticket */
+  const float* eps_dev;        /* [opt] device scalar overriding `eps` (lets a captured CUDA graph follow eps_rate_fn) */
 } DurfLossArgs;
 
 /* Slots of `partials` (per level: base = level * 8): sums before normalisation. */
@@ -260,12 +278,30 @@ typedef struct DurfLossArgs {
 #define DURF_LP_EMPTY  3
 #define DURF_LP_SKY    4
 #define DURF_LP_DISTR  5
+#define DURF_LP_OBJ    6   /* sum dyn_mask (rgb-px)^2   (obj_losses numerator, train_boxpose.py:192) */
+#define DURF_LP_DYN    7   /* sum dyn_mask              (obj_losses denominator) */
 #define DURF_LP_STRIDE 8
 
 /* Pass 1: masks and normalisers (sum lossmult, sum depth_mask, sum sky_mask) into norms[4].
  * Pass 2 (durf_losses_fwd_bwd): loss partial sums + gradients, using the normalisers. */
+int64_t durf_losses_reduce_ws_floats(int32_t B);
 int durf_losses_prepare(durf_stream_t stream, const DurfLossArgs* args, float* norms);
 int durf_losses_fwd_bwd(durf_stream_t stream, const DurfLossArgs* args, const float* norms);
+
+/* The scalar tail of loss_fn (train_boxpose.py:196-220) on the device: per-level losses from the sums and normalisers
+ * of the two passes above, and the weighted total.  stats = [num_levels][DURF_LS_STRIDE] {losses, d_losses, n_losses,
+ * e_losses, s_losses, distr_losses, obj_losses, tv_losses} followed by {loss, weight_l2}. */
+#define DURF_LS_STRIDE 8
+typedef struct DurfLossFinalizeArgs {
+  int32_t num_levels;
+  float coarse_loss_mult, depth_loss_mult, near_loss_mult, empty_loss_mult, sky_loss_mult, tv_loss_mult, distortion_mult;
+  const float* partials;       /* [num_levels * DURF_LP_STRIDE] */
+  const float* norms;          /* [num_levels * 4] */
+  const float* tv;             /* [opt] [num_levels] tv_losses = sum (pose - prev)^2 (train_boxpose.py:136) */
+  const float* weight_l2;      /* [opt] scalar (train_boxpose.py:72-74) */
+  float* stats;                /* [num_levels * DURF_LS_STRIDE + 2] */
+} DurfLossFinalizeArgs;
+int durf_losses_finalize(durf_stream_t stream, const DurfLossFinalizeArgs* args);
 
 /* ---- KA: gradient post-processing + Adam (train_boxpose.py:262-288) --------------------------- */
 /* nan_to_num(posinf=0) -> clip to +-max_val -> sum of squares into sumsq[0] (caller zeroes). */
@@ -274,6 +310,12 @@ int durf_grad_sanitize(durf_stream_t stream, int64_t n, float* grad, float max_v
  * doubles because they are Python floats in the reference: (1. - beta) is formed in double before it meets fp32. */
 int durf_adam_step(durf_stream_t stream, int64_t n, float* params, const float* grad, float* m, float* v,
                    const float* sumsq, float max_norm, float lr, double beta1, double beta2, double eps, int32_t step);
+/* The same update with the learning rate and the step counter read from DEVICE memory (a captured CUDA graph replays
+ * with a new lr / step without re-capture): lr_dev[0] = learning rate, step_dev[0] = 0-based step, incremented by the
+ * kernel when `advance_step` != 0.  The bias corrections 1 - beta^t are formed on the device in double like the host. */
+int durf_adam_step_dev(durf_stream_t stream, int64_t n, float* params, const float* grad, float* m, float* v,
+                       const float* sumsq, float max_norm, const float* lr_dev, int32_t* step_dev, int32_t advance_step,
+                       double beta1, double beta2, double eps);
 
 #ifdef __cplusplus
 }

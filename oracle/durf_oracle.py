@@ -625,7 +625,7 @@ def model_forward(params: Dict, rays: Rays, ext: Tensor, ts: int, randomized: bo
         else:
             dyn = hitf.sum(dim=-1)[..., None]
         ret.append(LevelOut(comp_rgb, distance, acc, weights, t_vals, t_mids, t_dists,
-                            (box_pose[0], box_rot), dyn, zo_ret))
+                            (box_pose[0], box_rot[0]), dyn, zo_ret))       # box_rot is [K,3]: the reference returns object 0's rotation
     return ret
 
 
