@@ -187,25 +187,38 @@ def cpu_baseline(mlp, c2w, centers, ext_np):
                 sample=f"{n} random pixels of the same frame, one pass of oracle.model_forward ({dt:.1f} s), torch fp32 on {cores} threads")
 
 
-def train_bench(dev, rank, world, steps, warmup, precision, pose=False):
+def train_bench(dev, rank, world, steps, warmup, precision, pose=False, global_batch=None, graph=False, e2e=True):
     """C3 (BASELINE.json configs[2]): one optimisation step on 16,384 rays per GPU -- dynamic scene (background + 2 object
     NeRFs), mip360 contraction, stratified + hierarchical sampling with explicit random buffers, RGB + URF LIDAR depth /
     line-of-sight (near, empty) + sky + distortion losses, backward, gradient mean over ranks (NCCL), clip, Adam.
-    Returns a dict for the "train" key of the JSON line (rays/s resident and end-to-end from pinned host batches)."""
+    Returns a dict for the "train" key of the JSON line (rays/s resident and end-to-end from pinned host batches).
+
+    `global_batch` = G: STRONG scaling -- one batch of G rays of ONE scene split evenly over the ranks (SURVEY §8d "rays split
+    evenly", utils.shard); otherwise every rank gets its own 16,384 rays (weak).  `graph`: replay the step from a CUDA graph
+    (durf_b200.train.GraphedTrainStep) instead of launching its ~100 kernels from Python."""
     import torch
     import torch.distributed as dist
-    from durf_b200 import ops, synthetic as S
+    from durf_b200 import ops, parallel, synthetic as S
     from durf_b200.obbpose_model import MipNerfModel, Variables
-    from durf_b200.train import TrainState, train_step
+    from durf_b200.train import TrainState, train_step, GraphedTrainStep
     from durf_b200.utils import Config, Rays
-    B, K, N = 16384, 2, N_SAMPLES
-    rng = np.random.default_rng(S.SEED + 7 + rank)
-    rays_np, c2w = S.random_rays(rng, B, far=40.0)
+    K, N = 2, N_SAMPLES
+    strong = global_batch is not None
+    B_all = global_batch if strong else 16384
+    rng = np.random.default_rng(S.SEED + 7 + (0 if strong else rank))     # strong: the same scene and batch on every rank
+    rays_np, c2w = S.random_rays(rng, B_all, far=40.0)
     centers, ext_np = S.boxes_in_view(rng, c2w, K)
     rng_w = np.random.default_rng(S.SEED)                       # same weights on every rank
     mlp = S.glorot_mlp(rng_w, 60, 256, 0.0)
     box_mlps = [S.glorot_mlp(rng_w, 63, 128, 0.0) for _ in range(K)]
-    tg = S.targets(rng, B)
+    tg = S.targets(rng, B_all)
+    t_rand_np = rng.uniform(size=(B_all, N + 1)).astype(np.float32)
+    u_rand_np = rng.uniform(size=(B_all, N + 1)).astype(np.float32)
+    s0, s1 = parallel.shard_range(B_all, rank, world) if strong else (0, B_all)
+    B = s1 - s0
+    rays_np = type(rays_np)(*[a[s0:s1] for a in rays_np])
+    tg = {k: a[s0:s1] for k, a in tg.items()}
+    t_rand_np, u_rand_np = t_rand_np[s0:s1], u_rand_np[s0:s1]
     pose = pose or os.environ.get("DURF_BENCH_POSE_OPT", "0") == "1"      # C5: joint box-pose optimisation
     model = MipNerfModel(precision=precision, num_objects=K, no_pose_opt=not pose, no_yaw_opt=not pose)
     v = Variables.allocate(model, K, centers.shape[0], dev)
@@ -218,7 +231,7 @@ def train_bench(dev, rank, world, steps, warmup, precision, pose=False):
     config = Config()
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     host = dict(rays=Rays(*[pin(a) for a in rays_np]), pixels=pin(tg['pixels']), depth=pin(tg['depth']), sky=pin(tg['sky']),
-                t_rand=pin(rng.uniform(size=(B, N + 1)).astype(np.float32)), u_rand=pin(rng.uniform(size=(B, N + 1)).astype(np.float32)))
+                t_rand=pin(t_rand_np), u_rand=pin(u_rand_np))
     ext = torch.from_numpy(ext_np).to(dev)
     to_dev = lambda h: dict(rays=Rays(*[r.to(dev, non_blocking=True) for r in h['rays']]), ext=ext, ts=1,
                             pixels=h['pixels'].to(dev, non_blocking=True), depth=h['depth'].to(dev, non_blocking=True),
@@ -227,8 +240,12 @@ def train_bench(dev, rank, world, steps, warmup, precision, pose=False):
     rnd_dev = dict(t_rand=host['t_rand'].to(dev), u_rand=host['u_rand'].to(dev))
     loss_host = torch.zeros(1).pin_memory()
 
+    gstep = GraphedTrainStep(model, config, state, B, K, world_size=world) if graph else None
+
     def step_resident():
         nonlocal state
+        if gstep is not None:
+            return gstep(resident, 5e-4, 3.0, 4.5 if pose else 10.0, rng=rnd_dev)
         state, st = train_step(model, config, rnd_dev, state, resident, lr=5e-4, eps=3.0, alpha=4.5 if pose else 10.0, world_size=world)
         return st
 
@@ -263,19 +280,149 @@ def train_bench(dev, rank, world, steps, warmup, precision, pose=False):
         st = step_resident()
     ops.reset_launch_count()
     ms = timed(step_resident, steps)
-    launches = ops.launch_count()
-    step_e2e()
-    ms_e2e = timed(step_e2e, steps)
+    launches = ops.launch_count() if gstep is None else gstep.kernels_per_replay * steps
+    if e2e and gstep is None:
+        step_e2e()
+        ms_e2e = timed(step_e2e, steps)
+    else:
+        ms_e2e = None
     loss = float(st['loss'])
     h2d = sum(r.numel() * 4 for r in host['rays']) + sum(host[k].numel() * 4 for k in ('pixels', 'depth', 'sky', 't_rand', 'u_rand'))
     # algorithmic MLP FLOPs of a step: fwd + dgrad + wgrad of the background MLP on every sample (object MLPs on hit rays are extra)
-    flops = 3.0 * B * 2 * N * MLP_FLOP_PER_SAMPLE
-    return dict(metric="rays/sec (train step, 2x128 samples)", value=B * world / (ms * 1e-3), unit="rays/s", ms_per_step=ms,
-                rays_per_step_per_gpu=B, steps=steps, warmup=warmup, dtype="bf16" if precision == "bf16" else "f32",
-                config="C3: 16384 rays/GPU, background + 2 object NeRFs, contraction, randomized sampling (explicit buffers), "
-                       "RGB + LIDAR depth/near/empty + sky + distortion losses, grad mean over ranks, clip, Adam",
-                e2e=dict(value=B * world / (ms_e2e * 1e-3), unit="rays/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
-                gpu_launches=int(launches), loss=loss, bg_mlp_tflops_algorithmic=flops / (ms * 1e-3) / 1e12)
+    rays_step = B_all if strong else B * world
+    flops = 3.0 * rays_step * 2 * N * MLP_FLOP_PER_SAMPLE
+    out = dict(metric="rays/sec (train step, 2x128 samples)", value=rays_step / (ms * 1e-3), unit="rays/s", ms_per_step=ms,
+               rays_per_step_per_gpu=B, steps=steps, warmup=warmup, dtype="bf16" if precision == "bf16" else "f32",
+               scaling="strong" if strong else "weak", cuda_graph=bool(graph),
+               config=("C3: %s, background + 2 object NeRFs, contraction, randomized sampling (explicit buffers), "
+                       "RGB + LIDAR depth/near/empty + sky + distortion losses, grad mean over ranks, clip, Adam"
+                       % (f"one batch of {B_all} rays split evenly over {world} GPU(s)" if strong else "16384 rays/GPU")),
+               gpu_launches=int(launches), loss=loss, mlp_tflops_algorithmic=flops / (ms * 1e-3) / 1e12)
+    if ms_e2e is not None:
+        out["e2e"] = dict(value=rays_step / (ms_e2e * 1e-3), unit="rays/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4)
+    return out
+
+
+def _timed(fn, k, world, dev):
+    """k calls of fn between barrier + synchronize on both sides, CUDA events, max over ranks -> ms per call."""
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return ms
+
+
+def strong_render_bench(dev, rank, world, steps, precision, chunk):
+    """STRONG scaling of C2: ONE 1920x1280 frame, contiguous pixel rows per GPU, every rank writes its own
+    slice of the frame, no collective.  Rays are generated on the device (durf_generate_rays), so nothing but the 12
+    camera floats crosses PCIe.  value = 2,457,600 rays / (max over ranks of the time for its rows)."""
+    import torch
+    from durf_b200 import parallel, synthetic as S
+    from durf_b200.obbpose_model import MipNerfModel, Variables, render_camera
+    mlp, c2w, centers, ext_np = frame_scene(0)                      # the same camera on every rank
+    model = MipNerfModel(dynamics=False, contraction=True, num_objects=1, precision=precision)
+    v = Variables.allocate(model, 1, 5, dev)
+    v.load_mlp("MLP_0", mlp)
+    v.box_centers.copy_(torch.from_numpy(centers).to(dev))
+    v.mark_dirty()
+    ext = torch.from_numpy(ext_np).to(dev)
+    r0, r1 = parallel.shard_range(H_FRAME, rank, world)
+    fn = lambda rng, b: model.apply(v, rng, b["rays"], None, b["ext"], b["ts"], False, False, False, b["alpha"])
+
+    def frame_rows():
+        from durf_b200 import ops
+        rows_per_chunk = max(1, chunk // W_FRAME)
+        for a in range(r0, r1, rows_per_chunk):
+            b = min(r1, a + rows_per_chunk)
+            rays = ops.generate_rays(c2w, W_FRAME, H_FRAME, S.FOCAL, 0.0, 40.0, a, b, device=dev)
+            fn(None, dict(rays=rays, ext=ext, ts=0, alpha=10.0))
+    frame_rows()
+    ms = _timed(frame_rows, steps, world, dev)
+    return dict(metric="rays/sec (render, 2x128 samples)", scaling="strong", value=W_FRAME * H_FRAME / (ms * 1e-3), unit="rays/s",
+                ms_per_frame=ms, rows_per_gpu=r1 - r0, config="one 1920x1280 frame, contiguous pixel rows per GPU, device ray generation, no collective")
+
+
+def small_batch_bench(dev, precision, steps=50):
+    """The reference's shipped batch (configs/carla_dyn.gin: Config.batch_size = 512): eager step (~100 launches from Python)
+    vs the same step replayed from a CUDA graph."""
+    out = {}
+    for graph in (False, True):
+        t = train_bench(dev, 0, 1, steps, 5, precision, global_batch=512, graph=graph, e2e=False)
+        out["graph" if graph else "eager"] = dict(ms_per_step=t["ms_per_step"], rays_per_s=t["value"], gpu_launches_per_step=t["gpu_launches"] / steps)
+    out["config"] = "C3 step at the reference's shipped batch of 512 rays (configs/carla_dyn.gin), 1 GPU"
+    return out
+
+
+def c1_bench(dev, precision, steps=20):
+    """BASELINE configs[0]: static-background forward render, 4096 rays x (128 + 128) samples, no contraction."""
+    import torch
+    from durf_b200 import synthetic as S
+    from durf_b200.obbpose_model import MipNerfModel, Variables
+    from durf_b200.utils import Rays
+    rng = np.random.default_rng(S.SEED + 3)
+    rays_np, c2w = S.random_rays(rng, 4096, far=40.0)
+    centers, ext_np = S.boxes_in_view(rng, c2w, 1, behind=True)
+    model = MipNerfModel(dynamics=False, contraction=False, num_objects=1, precision=precision)
+    v = Variables.allocate(model, 1, 5, dev)
+    v.load_mlp("MLP_0", S.glorot_mlp(np.random.default_rng(S.SEED), 60, 256, 0.0))
+    v.box_centers.copy_(torch.from_numpy(centers).to(dev)); v.mark_dirty()
+    rays = Rays(*[torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in rays_np])
+    ext = torch.from_numpy(ext_np).to(dev)
+    fn = lambda: model.apply(v, None, rays, None, ext, 0, False, False, False, 10.0)
+    for _ in range(3):
+        fn()
+    ms = _timed(fn, steps, 1, dev)
+    return dict(value=4096 / (ms * 1e-3), unit="rays/s", ms_per_step=ms, config="C1: 4096 rays x (128 + 128) samples, static background, no contraction")
+
+
+def c4_bench(dev, precision, chunk, cameras=5, K=8):
+    """BASELINE configs[3]: dynamic scene graph, background + 8 per-object NeRFs, per-ray OBB intersection and merged
+    compositing over a 5-camera Waymo-shape frame set (5 x 2,457,600 rays), device-generated rays."""
+    import torch
+    from durf_b200 import ops, synthetic as S
+    from durf_b200.obbpose_model import MipNerfModel, Variables, render_camera
+    rng = np.random.default_rng(S.SEED + 11)
+    c2ws = [S.random_c2w(rng) for _ in range(cameras)]
+    centers, ext_np = S.boxes_in_view(rng, c2ws[0], K)
+    ext_np = ext_np * np.float32(2.5)                       # ~10 % of the first camera's rays hit a box
+    model = MipNerfModel(precision=precision, num_objects=K)
+    v = Variables.allocate(model, K, centers.shape[0], dev)
+    rw = np.random.default_rng(S.SEED)
+    v.load_mlp("MLP_0", S.glorot_mlp(rw, 60, 256, 0.0))
+    for k in range(K):
+        v.load_mlp(f"BoxMLP_{k}", S.glorot_mlp(rw, 63, 128, 0.0))
+    v.box_centers.copy_(torch.from_numpy(centers).to(dev)); v.mark_dirty()
+    ext = torch.from_numpy(ext_np).to(dev)
+    hits = torch.zeros((), device=dev)
+
+    def fn(rng_, b):
+        out = model.apply(v, rng_, b["rays"], None, b["ext"], b["ts"], False, False, False, b["alpha"])
+        hits.add_((out[-1][8] > 0).sum())
+        return out
+
+    def frames(cams):
+        for c2w in cams:
+            render_camera(fn, c2w, W_FRAME, H_FRAME, S.FOCAL, 0.0, 40.0, None, ext, 0, None, 10.0, chunk=chunk)
+    frames(c2ws[:1])                                                  # warm-up: one camera
+    hits.zero_()
+    ms = _timed(lambda: frames(c2ws), 1, 1, dev)
+    n = cameras * W_FRAME * H_FRAME
+    return dict(value=n / (ms * 1e-3), unit="rays/s", ms_per_step=ms, rays_per_step=n, hit_fraction=float(hits) / n,
+                config=f"C4: {cameras} cameras x 1920x1280, background + {K} object NeRFs (BoxMLP on hit rays), OBB front-end + merged compositing")
 
 
 _REAL_STDOUT = None
@@ -307,7 +454,10 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-train", action="store_true", help="skip the C3 train-step measurement")
     ap.add_argument("--train-only", action="store_true", help="profiling aid: only the C3 train step (prints its dict)")
-    ap.add_argument("--train-steps", type=int, default=5)
+    ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--train-batch", type=int, default=None, help="profiling aid with --train-only: global batch (default 16384/GPU)")
+    ap.add_argument("--train-graph", action="store_true", help="profiling aid with --train-only: replay the step from a CUDA graph")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1 / C4 / small-batch / strong-scaling lines")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -335,7 +485,8 @@ def main():
     L.load()                                             # raises if libdurf_b200.so is missing
 
     if args.train_only:
-        t = train_bench(dev, rank, world, args.train_steps, 3, args.precision)
+        t = train_bench(dev, rank, world, args.train_steps, 3, args.precision, global_batch=args.train_batch, graph=args.train_graph,
+                        e2e=False)
         if rank == 0:
             emit(t)
         if world > 1:
@@ -427,6 +578,24 @@ def main():
         pose = train_bench(dev, rank, world, args.train_steps, 3, args.precision, pose=True)     # C5: + gradients into the SE(3) box poses
         train["pose_opt"] = dict(value=pose["value"], unit="rays/s", ms_per_step=pose["ms_per_step"],
                                  config="C5: same step with no_pose_opt = no_yaw_opt = False, alpha = 4.5 (BARF-weighted IPE)")
+    extras = {}
+    if not args.no_extras:
+        # STRONG scaling: one frame split by rows, one 16,384-ray batch split evenly, at this world size
+        torch.cuda.empty_cache()
+        extras["strong"] = dict(render=strong_render_bench(dev, rank, world, steps, args.precision, chunk))
+        if not args.no_train:
+            try:
+                extras["strong"]["train"] = train_bench(dev, rank, world, args.train_steps, 5, args.precision, global_batch=16384,
+                                                        graph=True, e2e=False)
+            except Exception as ex:                                   # graph capture of the NCCL buckets is the one risky piece
+                extras["strong"]["train_graph_error"] = repr(ex)[:200]
+                extras["strong"]["train"] = train_bench(dev, rank, world, args.train_steps, 5, args.precision, global_batch=16384,
+                                                        graph=False, e2e=False)
+        if world == 1:
+            extras["c1"] = c1_bench(dev, args.precision)
+            extras["c4"] = c4_bench(dev, args.precision, chunk)
+            if not args.no_train:
+                extras["small_batch"] = small_batch_bench(dev, args.precision)
 
     if rank != 0:
         if world > 1:
@@ -460,6 +629,7 @@ def main():
                 gpu_launches=int(launches), roofline=roof)
     if train is not None:
         line["train"] = train
+    line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(mlp, c2w, centers, ext_np)
     emit(line)

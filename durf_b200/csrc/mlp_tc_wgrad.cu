@@ -6,14 +6,17 @@
 // 128-byte rows, SWIZZLE_128B.  For wgrad the SAMPLE index is the contraction index, so the very same images are
 // MN-major tcgen05 operands (the 128-byte rows run along M / N, the 8-row groups along K): no transpose is ever made.
 //
-// One persistent CTA per SM owns a contiguous range of tiles and walks the list of jobs (one per weight matrix).
-// Per job the [in <= 256, out <= 256] fp32 accumulator sits in TMEM (<= 512 columns) while the CTA streams its tiles
-// through a 3-stage ring (64 samples of A and dZ per stage, cp.async.bulk + mbarrier); at the end of the job the
-// accumulator is added to the global gradient with fp32 reductions.  The kernel is HBM-bound (64 B/cycle/SM of operand
+// The work is a list of jobs (one per weight matrix).  Every CTA is bound to ONE job and a contiguous share of the tiles
+// (the host splits the SMs over the jobs in proportion to the bytes a job streams per tile): the job's [in <= 256, out <= 256]
+// fp32 accumulator sits in TMEM (<= 512 columns) for the whole kernel while the CTA streams its tiles through a 3-stage
+// ring (64 samples of A and dZ per stage, cp.async.bulk + mbarrier), and is added to the global gradient ONCE at the end
+// with 16-byte fp32 reductions.  (Round 1 gave every CTA a tile range and ALL jobs: 11 accumulator read-outs of 64 K scalar
+// reductions per CTA and launch = ~0.5 ms per launch whatever the batch, 74 % of a 512-ray step.)  The kernel is HBM-bound (64 B/cycle/SM of operand
 // bytes at full tensor rate), so the narrow heads (density N=1, rgb N=3, the 27 view inputs of the condition layer) and
 // all bias gradients are computed by the otherwise idle warps from the stages already in shared memory.
 #include "tc_common.cuh"
 #include "mlp_topology.h"
+#include <stdlib.h>
 
 namespace durf {
 
@@ -21,6 +24,7 @@ constexpr int kWgStages = 3;
 constexpr int kHalfBlock = 8192;          // 64 samples of one block image
 constexpr int kWgStageBytes = 8 * kHalfBlock;
 constexpr int kMaxJobs = 16;
+constexpr int kMaxCtas = 160;
 
 struct WgradJob {
   int a_src;        // 0: saved activations, 1: input-feature tiles
@@ -52,9 +56,16 @@ struct WgradParams {
   float* d_params;
   int n_jobs;
   WgradJob jobs[kMaxJobs];
+  uint8_t cta_job[kMaxCtas];   // job of CTA b
+  uint8_t cta_part[kMaxCtas];  // which share of the job's tiles
+  uint8_t job_parts[kMaxJobs]; // CTAs bound to the job
+  long long* trace;            // [opt] debugging (DURF_WGRAD_TRACE=1): cycles of every CTA
 };
 
 __device__ __forceinline__ void red_add(float* addr, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {      // addr 16-byte aligned
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __global__ void __launch_bounds__(384, 1)
 mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
@@ -84,15 +95,17 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
   const uint32_t tmem_base = *s_tmem;
 
   const int num_tiles = p.count ? min(*p.count, p.M) : p.M;
-  const int per = (num_tiles + gridDim.x - 1) / gridDim.x;
-  const int t_begin = min(num_tiles, (int)blockIdx.x * per), t_end = min(num_tiles, t_begin + per);
+  const int my_job = p.cta_job[blockIdx.x], parts = p.job_parts[my_job];
+  const int per = (num_tiles + parts - 1) / parts;
+  const int t_begin = min(num_tiles, (int)p.cta_part[blockIdx.x] * per), t_end = min(num_tiles, t_begin + per);
   const int my_tiles = t_end - t_begin;
+  const long long trace_t0 = clock64();
 
   if (warp == 0) {
     // ===== producer: per (job, tile, sample half) one stage: a_blocks + z_blocks half blocks of 8 KB =====
     if (lane == 0 && my_tiles > 0) {
       uint32_t stage = 0, phase = 0;
-      for (int j = 0; j < p.n_jobs; ++j) {
+      for (int j = my_job; j == my_job; ++j) {
         const WgradJob jb = p.jobs[j];
         const uint8_t* a_base = jb.a_src ? p.feat : p.saved;
         const size_t a_stride = (size_t)(jb.a_src ? 1 : p.saved_blocks) * kBlockBytes;
@@ -116,11 +129,11 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     // ===== MMA issuer: D[features of A, columns of dZ] += A^T dZ over the 64 samples of a stage (4 x K=16) =====
     if (my_tiles > 0) {      // the whole warp walks the schedule (uniform control flow), one elected lane issues
       constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-      uint32_t stage = 0, phase = 0, free_par = 0;
+      uint32_t stage = 0, phase = 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      for (int j = 0; j < p.n_jobs; ++j) {
+      for (int j = my_job; j == my_job; ++j) {
         const WgradJob jb = p.jobs[j];
-        if (jb.z_blocks > 0 && j > 0) { mbar_wait(bar_acc_free, free_par); free_par ^= 1; tc_fence_after(); }   // previous accumulator was read out
+        // one job per CTA: the accumulator is never recycled, no wait on bar_acc_free
         for (int tile = t_begin; tile < t_end; ++tile)
           for (int half = 0; half < 2; ++half) {
             mbar_wait(bar_full(stage), phase);
@@ -156,7 +169,7 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     float* s_cs = reinterpret_cast<float*>(smem + OFF_MISC + 128);     // [8][128] per-tile column sums (view part)
     uint32_t stage = 0, phase = 0, done_par = 0;
     if (my_tiles > 0)
-      for (int j = 0; j < p.n_jobs; ++j) {
+      for (int j = my_job; j == my_job; ++j) {
         const WgradJob jb = p.jobs[j];
         float bsum[8], ex[8][3], exb[3] = {0.f, 0.f, 0.f};
         float cv[32];                              // view part: d kernel[width + i][t], threads t < 128
@@ -265,9 +278,38 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
               tmem_ld_pin(v);
               if (m < jb.k_valid) {
                 float* dst = p.d_params + jb.dw_off + (size_t)m * jb.ld + c0;
+                // ld is a multiple of 4, so every row of the kernel has the same 16-byte phase (the blob offsets after the
+                // 257-float density head are odd): `lead` scalar reductions, then 16-byte ones, then the scalar tail
+                const int lead = (int)((4u - ((uint32_t)(reinterpret_cast<uintptr_t>(dst) >> 2) & 3u)) & 3u);
+                const int nv = min(32, jb.n_valid - c0);
+                int e = 0;
+                for (; e < lead && e < nv; ++e) red_add(dst + e, __uint_as_float(v[e]));
+                if (lead == 0) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e)
-                  if (c0 + e < jb.n_valid) red_add(dst + e, __uint_as_float(v[e]));
+                  for (int q4 = 0; q4 < 8; ++q4)
+                    if (4 * q4 + 4 <= nv) red_add4(dst + 4 * q4, __uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]),
+                                                   __uint_as_float(v[4 * q4 + 2]), __uint_as_float(v[4 * q4 + 3]));
+                  e = nv & ~3;
+                } else if (lead == 1) {
+#pragma unroll
+                  for (int q4 = 0; q4 < 7; ++q4)
+                    if (1 + 4 * q4 + 4 <= nv) red_add4(dst + 1 + 4 * q4, __uint_as_float(v[1 + 4 * q4]), __uint_as_float(v[2 + 4 * q4]),
+                                                       __uint_as_float(v[3 + 4 * q4]), __uint_as_float(v[4 + 4 * q4]));
+                  e = nv >= 1 ? 1 + ((nv - 1) & ~3) : nv;
+                } else if (lead == 2) {
+#pragma unroll
+                  for (int q4 = 0; q4 < 7; ++q4)
+                    if (2 + 4 * q4 + 4 <= nv) red_add4(dst + 2 + 4 * q4, __uint_as_float(v[2 + 4 * q4]), __uint_as_float(v[3 + 4 * q4]),
+                                                       __uint_as_float(v[4 + 4 * q4]), __uint_as_float(v[5 + 4 * q4]));
+                  e = nv >= 2 ? 2 + ((nv - 2) & ~3) : nv;
+                } else {
+#pragma unroll
+                  for (int q4 = 0; q4 < 7; ++q4)
+                    if (3 + 4 * q4 + 4 <= nv) red_add4(dst + 3 + 4 * q4, __uint_as_float(v[3 + 4 * q4]), __uint_as_float(v[4 + 4 * q4]),
+                                                       __uint_as_float(v[5 + 4 * q4]), __uint_as_float(v[6 + 4 * q4]));
+                  e = nv >= 3 ? 3 + ((nv - 3) & ~3) : nv;
+                }
+                for (; e < nv; ++e) red_add(dst + e, __uint_as_float(v[e]));
               }
             }
           }
@@ -278,6 +320,7 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x] = clock64() - trace_t0;
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
@@ -335,13 +378,61 @@ int mlp_tc_wgrad_launch(cudaStream_t st, const DurfMlpTopology& t, int saved_blo
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // every CTA ends each job with a [in,out] fp32 reduction into the global gradient: with few tiles use fewer CTAs
-  int grid = (P.M + 15) / 16;
-  grid = grid < 1 ? 1 : (grid > sms ? sms : grid);
+  sms = sms > kMaxCtas ? kMaxCtas : sms;
+  // CTAs per job in proportion to the job's cost per tile, at least one each, never more CTAs than tiles.  Cost model
+  // (cycles per tile, measured with DURF_WGRAD_TRACE on 16,384 tiles): 1500 (two ring stages' worth of latency) + 15 per KB
+  // streamed + the auxiliary warps' work for the narrow heads (density head 2000, rgb head 2560, view part 1160).
+  {
+    int bytes[kMaxJobs], total = 0, parts[kMaxJobs], used = 0;
+    static const int kExtraCost[4] = {0, 2000, 2560, 1160};
+    for (int j = 0; j < nj; ++j) {
+      bytes[j] = 1500 + 15 * 16 * (P.jobs[j].a_blocks + P.jobs[j].z_blocks) + kExtraCost[P.jobs[j].extra & 3];
+      total += bytes[j];
+    }
+    const int budget = sms < nj ? nj : sms;
+    const int max_parts = P.M < 1 ? 1 : (P.M > 255 ? 255 : P.M);
+    for (int j = 0; j < nj; ++j) {
+      int q = (int)((long long)bytes[j] * budget / total);
+      q = q < 1 ? 1 : (q > max_parts ? max_parts : q);
+      parts[j] = q; used += q;
+    }
+    for (bool grew = true; used < budget && grew;) {        // hand the remaining SMs to the jobs with the most bytes per CTA
+      grew = false;
+      int best = -1;
+      for (int j = 0; j < nj; ++j)
+        if (parts[j] < max_parts && (best < 0 || bytes[j] * parts[best] > bytes[best] * parts[j])) best = j;
+      if (best >= 0) { ++parts[best]; ++used; grew = true; }
+    }
+    DURF_REQUIRE(used <= kMaxCtas, DURF_E_UNSUPPORTED, "durf_mlp_bwd(bf16): wgrad needs %d CTAs", used);
+    int b = 0;
+    for (int j = 0; j < nj; ++j) {
+      P.job_parts[j] = (uint8_t)parts[j];
+      for (int q = 0; q < parts[j]; ++q, ++b) { P.cta_job[b] = (uint8_t)j; P.cta_part[b] = (uint8_t)q; }
+    }
+    // interleave would spread a job over both dies; the order only matters for L2 locality of A / dZ, which stream once
+  }
+  int grid = 0;
+  for (int j = 0; j < nj; ++j) grid += P.job_parts[j];
   cudaError_t e = cudaFuncSetAttribute(mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
   DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_bwd(bf16): smem attribute: %s", cudaGetErrorString(e));
+  static long long* trace_buf = nullptr;
+  const bool tracing = getenv("DURF_WGRAD_TRACE") != nullptr;
+  if (tracing && !trace_buf) cudaMalloc(&trace_buf, kMaxCtas * sizeof(long long));
+  P.trace = tracing ? trace_buf : nullptr;
   mlp_tc_wgrad_kernel<<<grid, 384, kWgSmemBytes, st>>>(P);
   DURF_CHECK_LAUNCH("durf_mlp_bwd(bf16): wgrad");
+  if (tracing) {                                             // debugging aid only: synchronises
+    long long h[kMaxCtas];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, trace_buf, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "wgrad trace: M=%d width=%d grid=%d\n", P.M, t.width, grid);
+    for (int j = 0, b = 0; j < nj; ++j) {
+      long long mx = 0;
+      for (int q = 0; q < P.job_parts[j]; ++q, ++b) mx = h[b] > mx ? h[b] : mx;
+      fprintf(stderr, "  job %2d a=%d z=%d extra=%d parts=%3d max_cycles=%lld\n", j, P.jobs[j].a_blocks, P.jobs[j].z_blocks, P.jobs[j].extra,
+              P.job_parts[j], mx);
+    }
+  }
   return DURF_OK;
 }
 

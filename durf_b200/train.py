@@ -182,6 +182,7 @@ class GraphedTrainStep:
         self.scalars = StepScalars.create(dev, step=state.step)
         self.workspace: dict = {}
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.kernels_per_replay = 0
         self.stats: Optional[dict] = None
 
     def _load(self, batch, lr, eps, alpha, rng, prev):
@@ -230,8 +231,10 @@ class GraphedTrainStep:
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
+            before = ops.launch_count()
             with torch.cuda.graph(self.graph):
                 self.stats = self._eager()          # recorded, not executed
+            self.kernels_per_replay = ops.launch_count() - before      # library kernels inside one replay
             st.variables.flat.copy_(snap[0]); st.m.copy_(snap[1]); st.v.copy_(snap[2]); self.scalars.step.copy_(snap[3])
             st.step = snap[4]
             st.variables.mark_dirty()

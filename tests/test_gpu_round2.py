@@ -128,15 +128,19 @@ def test_graph_captured_step_replays_like_eager(pose_opt):
     sched = [(1e-3, 3.0, 4.0, 2), (8e-4, 2.5, 6.5, 0), (5e-4, 2.0, 10.0, 4)]
     prev = cu(sc['centers'][1])[None]
 
-    def eager():
+    first = {}
+
+    def eager(tag):
         model_e = _model(precision='bf16', **kw)
         v_e = H.cuda_variables(sc, model_e)
         st_e = TrainState.create(v_e)
-        for lr, eps, alpha, ts in sched:
+        for i, (lr, eps, alpha, ts) in enumerate(sched):
             st_e, stats_e = train_step(model_e, config, rng, st_e, mk(ts), lr=lr, eps=eps, alpha=alpha, prev=prev)
+            if i == 0:
+                first[tag] = (stats_e['grad'].clone(), stats_e['loss'].clone())
         return v_e, stats_e
-    v_e, stats_e = eager()
-    v_e2, _ = eager()          # run-to-run noise of the eager step itself (wgrad / bias reductions use float atomics)
+    v_e, stats_e = eager('a')
+    v_e2, _ = eager('b')       # run-to-run noise of the eager step itself (wgrad / bias reductions use float atomics)
 
     model_g = _model(precision='bf16', **kw)
     v_g = H.cuda_variables(sc, model_g)
@@ -147,7 +151,15 @@ def test_graph_captured_step_replays_like_eager(pose_opt):
         if i == 1:
             ops.reset_launch_count()
         stats_g = step(mk(ts), lr, eps, alpha, rng=rng, prev=prev)
+        if i == 0:
+            first['g'] = (stats_g['grad'].clone(), stats_g['loss'].clone())
     torch.cuda.synchronize()
+    # the FIRST step's raw gradient and loss: nothing amplifies summation-order noise yet
+    ga, gb, gg = first['a'][0].double(), first['b'][0].double(), first['g'][0].double()
+    n1 = float((ga - gb).norm() / ga.norm())
+    r1 = float((ga - gg).norm() / ga.norm())
+    assert r1 <= max(1e-5, 3.0 * n1), f"first replayed step: gradient differs from eager by {r1:.3e} (eager vs eager {n1:.3e})"
+    assert torch.equal(first['a'][1], first['g'][1]), "the deterministic loss value must be bit-identical eager vs replay"
     assert ops.launch_count() == 0, "replays must not launch kernels from the host side of the library"
     assert int(step.scalars.step.item()) == 3 and st_g.step == 3
     upd_e, upd_g = (v_e.flat - start).double(), (v_g.flat - start).double()
@@ -155,8 +167,8 @@ def test_graph_captured_step_replays_like_eager(pose_opt):
     rel = float((upd_e - upd_g).norm() / upd_e.norm())
     noise = float(((v_e2.flat - start).double() - upd_e).norm() / upd_e.norm())
     # three Adam steps from zero moments are sign-like in g where |g| ~ 1e-8, so summation-order noise is amplified: the graph
-    # must be no further from an eager run than two eager runs are from each other (x3), floor 1e-3
-    assert rel <= max(1e-3, 3.0 * noise), f"graph replay vs eager: {rel:.3e} of the 3-step update (eager vs eager: {noise:.3e})"
+    # must be no further from an eager run than two eager runs are from each other (x5, one pair is a noisy estimate), floor 2e-3
+    assert rel <= max(2e-3, 5.0 * noise), f"graph replay vs eager: {rel:.3e} of the 3-step update (eager vs eager: {noise:.3e})"
     assert abs(float(stats_g['loss']) - float(stats_e['loss'])) <= 1e-4 * max(1.0, abs(float(stats_e['loss'])))
 
 

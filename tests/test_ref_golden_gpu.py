@@ -316,7 +316,8 @@ def test_train_step_fp32_against_reference(name):
     grad = stats['grad'].double().cpu().numpy()
     names = C.param_names(sc['K'])
     slices = _named_slices(v, sc)
-    tol = 1e-2         # SURVEY §7 asks cosine >= 0.999 per tensor, i.e. |dg|/|g| <= 4.5e-2; we hold 1e-2 (cosine >= 0.99995)
+    tol = 2e-2         # SURVEY §7 asks cosine >= 0.999 per tensor, i.e. |dg|/|g| <= 4.5e-2; we hold 2e-2 (cosine >= 0.9998);
+    #                    the large tensors agree to ~1e-3, the loosest are first-layer biases of object MLPs with |g| ~ 4e-5
     for i, n in enumerate(names):
         off, cnt = slices[n]
         gr = grad[off:off + cnt]
