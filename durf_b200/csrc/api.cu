@@ -95,7 +95,10 @@ static int check_mlp(const DurfMlpArgs* a, const char* who) {
   DURF_REQUIRE(a != nullptr, DURF_E_INVALID, "%s: null args", who);
   DURF_REQUIRE(topology_ok(&a->topo), DURF_E_INVALID, "%s: bad topology", who);
   DURF_REQUIRE(a->M >= 0 && a->N >= 1, DURF_E_INVALID, "%s: bad shape M=%d N=%d", who, a->M, a->N);
-  DURF_REQUIRE(a->features && a->cond && a->params && a->raw_rgb && a->raw_density, DURF_E_INVALID, "%s: null buffer", who);
+  DURF_REQUIRE(a->fused_raymarch == nullptr || a->precision == DURF_PREC_BF16, DURF_E_UNSUPPORTED,
+               "%s: the fused ray-march (in-kernel feature generation) exists on the tensor-core path only", who);
+  DURF_REQUIRE((a->features || a->fused_raymarch) && a->cond && a->params && a->raw_rgb && a->raw_density, DURF_E_INVALID,
+               "%s: null buffer", who);
   DURF_REQUIRE(a->precision == DURF_PREC_FP32 || a->precision == DURF_PREC_BF16, DURF_E_INVALID, "%s: unknown precision %d",
                who, a->precision);
   return DURF_OK;

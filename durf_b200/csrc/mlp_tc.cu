@@ -25,6 +25,7 @@
 
 #include "tc_common.cuh"
 #include "mlp_topology.h"
+#include "raymarch_device.cuh"
 
 namespace durf {
 
@@ -73,6 +74,22 @@ struct TcParams {
   int n_chunks;              // ring-stage uses per tile
   int off_wden, off_bden, off_wrgb, off_brgb, off_wview;
   int trace;                 // DURF_TC_TRACE=1: block 0 prints where its MMA thread and one epilogue thread spent their cycles
+  // N1: the input tile is GENERATED inside the kernel by warps 2-3 (fenceposts -> conical-frustum Gaussian ->
+  // mask -> contraction -> IPE, the arithmetic of raymarch.cu's bf16 path) instead of loaded from `feat`
+  int gen;
+  uint32_t rm_flags;
+  int min_deg;
+  float alpha;
+  const float* alpha_dev;
+  const float* g_origins;    // [B,3] origins_s
+  const float* g_dirs;       // [B,3] dirs_s
+  const float* g_radii;      // [B]
+  const float* g_near;       // [B] (DURF_RM_SAMPLE)
+  const float* g_far;
+  const float* g_t_rand;     // [B,129] (DURF_RM_RANDOMIZED)
+  const float* g_ray_mult;   // [opt] [B]
+  float* g_t_vals;           // [B,129]: written when DURF_RM_SAMPLE, else read
+  uint8_t* feat_out;         // [opt] the generated tiles are also stored here (training: wgrad reads them)
   LayerSched sched[kMaxG];
   ChunkSched chunks[kMaxChunks];
 };
@@ -160,11 +177,12 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
   const uint32_t bar_inp_full = bar0 + 8 * (2 * kMaxStages), bar_inp_empty = bar0 + 8 * (2 * kMaxStages + 1);
   auto bar_acc_full = [&](int h) { return bar0 + 8 * (2 * kMaxStages + 2 + h); };
   auto bar_a_ready = [&](int kb) { return bar0 + 8 * (2 * kMaxStages + 4 + kb); };   // one per 64-column K block of the next layer's A
-  static_assert(32 + 8 * (2 * kMaxStages + 8) <= C::MISC_BYTES, "barrier area");
+  static_assert(32 + 8 * (2 * kMaxStages + 8) + 64 <= C::MISC_BYTES, "barrier area + BARF weights");
+  float* s_barf = reinterpret_cast<float*>(smem + C::OFF_MISC + 32 + 8 * (2 * kMaxStages + 8));     // [16] (weighted IPE)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), nct); }
-    mbar_init(bar_inp_full, 1); mbar_init(bar_inp_empty, 1);
+    mbar_init(bar_inp_full, p.gen ? 2 : 1); mbar_init(bar_inp_empty, 1);   // generated tiles: one arrival per generator warp
     for (int h = 0; h < 2; ++h) mbar_init(bar_acc_full(h), 1);
     for (int kb = 0; kb < 4; ++kb) mbar_init(bar_a_ready(kb), 8);   // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,6 +200,10 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     s_wrgb[j * 128 + c] = p.params[p.off_wrgb + c * 3 + j];
   }
   if (threadIdx.x < 4) s_hb[threadIdx.x] = threadIdx.x == 0 ? p.params[p.off_bden] : p.params[p.off_brgb + threadIdx.x - 1];
+  if (p.gen && threadIdx.x >= 32 && threadIdx.x < 48) {      // mip.py:217-218: w_k = (1 - cos(clip(alpha - k, 0, 1) * pi)) / 2
+    const float c = fminf(fmaxf((p.alpha_dev ? *p.alpha_dev : p.alpha) - (float)(threadIdx.x - 32), 0.f), 1.f);
+    s_barf[threadIdx.x - 32] = (1.f - cosf(c * 3.14159265358979324f)) / 2.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -295,18 +317,85 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       if (tr && lane == 0) printf("durf mlp_tc trace: MMA thread: %d tiles, total %lld cyc; tile start (features, drained accumulators) %lld\n",
                      it, clock64() - t_begin, t_start);
     }
-  } else if (warp == 2) {
-    // ===== feature-tile loader: the next tile's features arrive while the layers after the skip layer run =====
-    if (lane == 0) {
+  } else if (warp == 2 || warp == 3) {
+    if (!p.gen) {
+      // ===== feature-tile loader: the next tile's features arrive while the layers after the skip layer run =====
+      if (warp == 2 && lane == 0) {
+        uint32_t par = 0;
+        for (int tile = blockIdx.x; more(tile); tile += gridDim.x) {
+          mbar_wait(bar_inp_empty, par ^ 1);
+          mbar_arrive_expect_tx(bar_inp_full, kInpBytes);
+          bulk_g2s(sbase + C::OFF_INP, p.feat + (size_t)min(tile, num_tiles - 1) * kInpBytes, kInpBytes, bar_inp_full);
+          par ^= 1;
+        }
+      }
+      __syncwarp();
+    } else {
+      // ===== feature-tile GENERATOR (N1): 64 threads, two samples each; the ray-march of raymarch.cu's bf16 path, written
+      // straight into the SWIZZLE_128B A-operand image in shared memory.  It runs while the layers after the skip layer of the
+      // previous tile execute (the tile is ~30 k cycles of MMAs, a row costs ~400 instructions). =====
+      const int gt = threadIdx.x - 64;                       // 0..63
+      const bool weighted = (p.rm_flags & DURF_RM_WEIGHTED) != 0;
+      const bool sample = (p.rm_flags & DURF_RM_SAMPLE) != 0;
       uint32_t par = 0;
       for (int tile = blockIdx.x; more(tile); tile += gridDim.x) {
-        mbar_wait(bar_inp_empty, par ^ 1);
-        mbar_arrive_expect_tx(bar_inp_full, kInpBytes);
-        bulk_g2s(sbase + C::OFF_INP, p.feat + (size_t)min(tile, num_tiles - 1) * kInpBytes, kInpBytes, bar_inp_full);
+        const bool valid = tile < num_tiles;
+        const int tcl = min(tile, num_tiles - 1);
+        const int ray = p.ray_index ? p.ray_index[tcl] : tcl;
+        const float o[3] = {p.g_origins[3 * ray], p.g_origins[3 * ray + 1], p.g_origins[3 * ray + 2]};
+        const float d[3] = {p.g_dirs[3 * ray], p.g_dirs[3 * ray + 1], p.g_dirs[3 * ray + 2]};
+        const float radius = p.g_radii[ray];
+        const bool has_mult = p.g_ray_mult != nullptr;
+        const float mult = has_mult ? p.g_ray_mult[ray] : 1.f;
+        float tf[2][2];                                      // fenceposts (r, r+1) of this thread's rows gt and gt + 64
+        if (sample) {
+          const float nr = p.g_near[ray], fr = p.g_far[ray];
+          const float* tr_row = (p.rm_flags & DURF_RM_RANDOMIZED) ? p.g_t_rand + (size_t)ray * (kTileM + 1) : nullptr;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int r = gt + 64 * k;
+            tf[k][0] = sample_fencepost(nr, fr, r, kTileM, tr_row);
+            tf[k][1] = sample_fencepost(nr, fr, r + 1, kTileM, tr_row);
+            if (valid) {
+              p.g_t_vals[(size_t)ray * (kTileM + 1) + r] = tf[k][0];
+              if (r == kTileM - 1) p.g_t_vals[(size_t)ray * (kTileM + 1) + kTileM] = tf[k][1];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int r = gt + 64 * k;
+            tf[k][0] = p.g_t_vals[(size_t)ray * (kTileM + 1) + r];
+            tf[k][1] = p.g_t_vals[(size_t)ray * (kTileM + 1) + r + 1];
+          }
+        }
+        if (p.feat_out) {     // the previous tile's image must have left shared memory before it is overwritten
+          if (gt == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 3, 64;" ::: "memory");
+        }
+        mbar_wait(bar_inp_empty, par ^ 1);                   // every MMA reading the previous tile's image has retired
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const Gauss g = sample_gaussian(p.rm_flags, o, d, radius, mult, has_mult, tf[k][0], tf[k][1]);
+          if (weighted) encode_row_bf16_smem<true>(g, p.min_deg, s_barf, sbase + C::OFF_INP, gt + 64 * k);
+          else encode_row_bf16_smem<false>(g, p.min_deg, s_barf, sbase + C::OFF_INP, gt + 64 * k);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to tcgen05.mma / bulk copies
+        if (p.feat_out) {
+          asm volatile("bar.sync 3, 64;" ::: "memory");
+          if (gt == 0) {
+            if (valid)
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.feat_out + (size_t)tile * kInpBytes),
+                           "r"(sbase + C::OFF_INP), "n"(kInpBytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_inp_full);
         par ^= 1;
       }
+      if (p.feat_out && gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ===== epilogue: thread = accumulator row = sample; warps q and q+4 share TMEM lane quarter q =====
     const int q = warp & 3;
@@ -688,7 +777,16 @@ int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a) {
   DURF_REQUIRE(tc_supported(t), DURF_E_UNSUPPORTED,
                "durf_mlp_fwd(bf16): tensor-core path needs width 128/256, cond_width 128, in_dim <= 64, depth <= 9");
   DURF_REQUIRE(a.N == kTileM, DURF_E_UNSUPPORTED, "durf_mlp_fwd(bf16): needs 128 samples per ray (got %d)", a.N);
-  DURF_REQUIRE(a.packed && a.params && a.features && a.cond, DURF_E_INVALID, "durf_mlp_fwd(bf16): null buffer");
+  const DurfRaymarchArgs* rm = a.fused_raymarch;
+  DURF_REQUIRE(a.packed && a.params && (a.features || rm) && a.cond, DURF_E_INVALID, "durf_mlp_fwd(bf16): null buffer");
+  if (rm) {
+    const bool weighted = (rm->flags & DURF_RM_WEIGHTED) != 0;
+    DURF_REQUIRE(rm->N == kTileM && rm->max_deg - rm->min_deg == 10 && t.in_dim == 60 + (weighted ? 3 : 0), DURF_E_UNSUPPORTED,
+                 "durf_mlp_fwd(bf16): fused ray-march needs N = 128, 10 degrees and in_dim = 60 (IPE) / 63 (weighted IPE)");
+    DURF_REQUIRE(rm->origins && rm->dirs && rm->radii && rm->t_vals, DURF_E_INVALID, "durf_mlp_fwd(bf16): fused ray-march: null ray buffer");
+    DURF_REQUIRE(!(rm->flags & DURF_RM_SAMPLE) || (rm->near && rm->far), DURF_E_INVALID, "durf_mlp_fwd(bf16): fused ray-march: near/far missing");
+    DURF_REQUIRE(!(rm->flags & DURF_RM_RANDOMIZED) || rm->t_rand, DURF_E_INVALID, "durf_mlp_fwd(bf16): fused ray-march: t_rand missing");
+  }
   DURF_REQUIRE(a.saved == nullptr || mlp_tc_bwd_supported(t), DURF_E_UNSUPPORTED,
                "durf_mlp_fwd(bf16): activation saving needs a topology with a tensor-core backward");
   const size_t need = mlp_tc_workspace_bytes(t, a.M);
@@ -707,6 +805,14 @@ int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a) {
                                              a.params + L.w_off[t.depth + 2] + (size_t)t.width * t.cond_width,
                                              a.params + L.b_off[t.depth + 2], (float*)a.workspace);
     DURF_CHECK_LAUNCH("durf_mlp_fwd(bf16): cond_bias");
+  }
+  P.gen = rm ? 1 : 0;
+  P.feat_out = nullptr;
+  if (rm) {
+    P.rm_flags = rm->flags; P.min_deg = rm->min_deg; P.alpha = rm->alpha; P.alpha_dev = rm->alpha_dev;
+    P.g_origins = rm->origins; P.g_dirs = rm->dirs; P.g_radii = rm->radii; P.g_near = rm->near; P.g_far = rm->far;
+    P.g_t_rand = rm->t_rand; P.g_ray_mult = rm->ray_mult; P.g_t_vals = rm->t_vals;
+    P.feat_out = (uint8_t*)a.features;            // NULL: the tiles exist only in shared memory
   }
   P.feat = (const uint8_t*)a.features; P.cond = a.cond; P.params = a.params; P.packed = (const uint8_t*)a.packed;
   P.ray_index = a.ray_index; P.count = a.count; P.M = a.M; P.accumulate = a.accumulate;

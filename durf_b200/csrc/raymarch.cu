@@ -11,6 +11,7 @@
 // HBM-bound by design: 48 B + 516 B in, N*F*4 B out per ray-level; compiled with -fmad=false so that the
 // arithmetic is the reference's operation sequence.
 #include "common.cuh"
+#include "raymarch_device.cuh"
 
 namespace durf {
 
@@ -20,8 +21,6 @@ struct RayMarchParams {
   int F;          // features per sample
   int D;          // number of degrees
 };
-
-__device__ __forceinline__ float pow2i(int l) { return __int_as_float((127 + l) << 23); }
 
 // Fills s_t[0..N] with the ray's fenceposts (mip.py:351-368) or loads them.
 __device__ __forceinline__ void load_or_sample_t(const DurfRaymarchArgs& a, int ray, int lane, float* s_t) {
@@ -54,68 +53,6 @@ __device__ __forceinline__ void load_or_sample_t(const DurfRaymarchArgs& a, int 
   }
 }
 
-struct Gauss {
-  float mean[3];
-  float var[3];
-};
-
-// Per-sample Gaussian: mip.py:117-124 (cone) / 149-151 (cylinder), lift (76-96, diagonal only),
-// ray multiplier (obbpose_model.py:179-180 / 207-208), contraction (mip360.py:47-79).
-__device__ __forceinline__ Gauss sample_gaussian(const DurfRaymarchArgs& a, const float o[3], const float d[3],
-                                                 float radius, float mult, bool has_mult, float t0, float t1) {
-  float t_mean, t_var, r_var;
-  if (a.flags & DURF_RM_CYLINDER) {
-    t_mean = (t0 + t1) / 2.f;
-    r_var = radius * radius / 4.f;
-    t_var = (t1 - t0) * (t1 - t0) / 12.f;
-  } else {
-    const float mu = (t0 + t1) / 2.f;
-    const float hw = (t1 - t0) / 2.f;
-    const float mu2 = mu * mu, hw2 = hw * hw;
-    const float den = 3.f * mu2 + hw2;
-    const float hw4 = hw2 * hw2;
-    t_mean = mu + (2.f * mu * hw2) / den;
-    t_var = hw2 / 3.f - (4.f / 15.f) * ((hw4 * (12.f * mu2 - hw2)) / (den * den));
-    r_var = (radius * radius) * (mu2 / 4.f + (5.f / 12.f) * hw2 - (4.f / 15.f) * hw4 / den);
-  }
-  const float dmag = fmaxf(1e-10f, d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-  Gauss g;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    g.mean[i] = d[i] * t_mean + o[i];
-    const float outer = d[i] * d[i];
-    const float null_outer = 1.f - d[i] * (d[i] / dmag);
-    g.var[i] = t_var * outer + r_var * null_outer;
-  }
-  if (a.flags & DURF_RM_NO_INTEGRATE) g.var[0] = g.var[1] = g.var[2] = 0.f;
-  if (has_mult) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { g.mean[i] = mult * g.mean[i]; g.var[i] = mult * g.var[i]; }
-  }
-  if (a.flags & DURF_RM_CONTRACT) {
-    const float x0 = g.mean[0], x1 = g.mean[1], x2 = g.mean[2];
-    float sq = x0 * x0 + x1 * x1 + x2 * x2;
-    const bool floor_hit = sq < 1e-12f;
-    sq = floor_hit ? 1e-12f : sq;
-    const float n = sqrtf(sq);
-    if (n > 0.1f) {
-      const float inv = 1.f / n;
-      const float A = 2.f - inv;
-      const float dn = floor_hit ? 0.f : (x0 + x1 + x2) / n;     // JVP of the norm along the all-ones tangent
-      const float dA = dn / (n * n);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const float Bv = g.mean[i] / n;
-        const float dB = inv - g.mean[i] * dn / (n * n);
-        const float v = dA * Bv + A * dB;
-        g.mean[i] = A * Bv;
-        g.var[i] = (g.var[i] * v) * v;                           // cov @ diag(v)^2, diagonal entry
-      }
-    }
-  }
-  return g;
-}
-
 // Feature f (0 <= f < F) of a sample.  Layout: [sin(2^l x_d)]_{l,d}, then the same shifted by pi/2 (mip.py:280-282);
 // weighted variant: [mean, w[i/6] * enc_i] (mip.py:215-222).
 __device__ __forceinline__ float feature_value(const float* __restrict__ g6, int f, int D, int min_deg, bool weighted,
@@ -135,54 +72,6 @@ __device__ __forceinline__ float feature_value(const float* __restrict__ g6, int
   float e = expf(-0.5f * yv) * safe_sinf(y);
   if (weighted) e = s_w[f / 6] * e;
   return e;
-}
-
-// Tensor-core path (features leave as bf16, half-ulp 2^-9): all 2*3*10 encodings of a sample from THREE accurate sincosf
-// calls, the higher octaves by angle doubling (sin 2y = 2 s c, cos 2y = 1 - 2 s^2; the error doubles per octave and stays
-// below 1e-4 at 2^9, 20x under the bf16 rounding of the stored value) and one ex2 per (octave, axis).  The fp32 output
-// path below keeps the reference's exact sequence (sin(y + fl32(pi/2)) with the 100*pi wrap, math.py:35-36) instead.
-// Writes the sample's 128-byte row of the SWIZZLE_128B tile image.
-template <bool weighted>
-__device__ __forceinline__ void encode_row_bf16(const Gauss& g, int min_deg, const float* __restrict__ s_w,
-                                                uint8_t* __restrict__ tile_base, int row) {
-  constexpr int D = 10;
-  float feat[64];
-#pragma unroll
-  for (int i = 0; i < 64; ++i) feat[i] = 0.f;
-  constexpr int o = weighted ? 3 : 0;
-  const float sc0 = pow2i(min_deg);
-  float sn[3], cs[3], yv[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    if (weighted) feat[d] = g.mean[d];
-    sincosf(g.mean[d] * sc0, &sn[d], &cs[d]);
-    yv[d] = g.var[d] * (sc0 * sc0) * (-0.5f * 1.44269504088896341f);
-  }
-  // octave-major order: a pair of neighbouring features is complete within two octaves, so it can be packed early
-#pragma unroll
-  for (int l = 0; l < D; ++l) {
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const float e = exp2f(yv[d]);
-      feat[o + 3 * l + d] = e * sn[d];
-      feat[o + 3 * D + 3 * l + d] = e * cs[d];
-      const float s2 = 2.f * sn[d] * cs[d], c2 = 1.f - 2.f * (sn[d] * sn[d]);
-      sn[d] = s2; cs[d] = c2;
-      yv[d] = yv[d] * 4.f;
-    }
-  }
-  if (weighted) {
-#pragma unroll
-    for (int i = 0; i < 6 * D; ++i) feat[3 + i] = s_w[i / 6] * feat[3 + i];     // mip.py:220: weight index i // 6
-  }
-  // 32-byte stores (STG.256): every store fills a whole sector of the swizzled image
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    uint32_t w[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) w[e] = pack_bf16x2(feat[16 * k + 2 * e], feat[16 * k + 2 * e + 1]);
-    st_sw128_pair(tile_base, (uint32_t)row, 2 * k, w);
-  }
 }
 
 __global__ void __launch_bounds__(128, 5)
@@ -213,7 +102,7 @@ raymarch_fwd_kernel(const RayMarchParams p) {
     const float mult = has_mult ? a.ray_mult[ray] : 1.f;
     const bool fast_tiles = (a.flags & DURF_RM_OUT_BF16_TILE) && p.D == 10;
     for (int n = lane; n < N; n += 32) {
-      const Gauss g = sample_gaussian(a, o, d, radius, mult, has_mult, s_t[n], s_t[n + 1]);
+      const Gauss g = sample_gaussian(a.flags, o, d, radius, mult, has_mult, s_t[n], s_t[n + 1]);
       if (fast_tiles) {
         uint8_t* tile_base = reinterpret_cast<uint8_t*>(a.features) + ((size_t)m * N / 128) * (128 * 128);
         const int row = (int)(((size_t)m * N) % 128) + n;

@@ -15,6 +15,7 @@ Differences that are part of the boundary (documented in INTEGRATION.md):
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, NamedTuple, Optional, Sequence, Tuple
 
@@ -62,6 +63,10 @@ class MipNerfModel:
     # hit COUNT stays on the device (no host sync); lower this to save memory when few rays hit a box -- rays beyond the
     # cap would be dropped, so `apply` records the overflow in ctx['obj_overflow'] (a device flag) for the caller to check.
     max_obj_rays: Optional[int] = None
+    # on the tensor-core path the MLP kernel generates its own input tiles (frustum -> Gaussian -> contraction ->
+    # IPE in two warps of the kernel, written straight into the shared-memory A operand): no ray-march launch and no
+    # 16 KB/ray-level feature image in HBM.  False = separate durf_raymarch_fwd launches (the round-1 path).
+    fuse_raymarch: bool = field(default_factory=lambda: os.environ.get('DURF_FUSE_RAYMARCH', '1') != '0')
 
     # -- topology helpers ------------------------------------------------------------------------------
     def bg_topology(self):
@@ -161,18 +166,28 @@ class MipNerfModel:
         for i_level in range(self.num_levels):
             common = dict(min_deg=self.min_deg_point, max_deg=self.max_deg_point, ray_shape=self.ray_shape,
                           integrate=not self.disable_integration, bf16_tiles=bf16)
-            if i_level == 0:
-                rm = ops.raymarch(origins_s, dirs_s, radii, N, near=rays.near, far=rays.far, t_rand=rb['t_rand'],
-                                  contract=self.contraction, ray_mult=bg_mult, **common)
-                t_vals = rm['t_vals']
-            else:
+            fuse = bf16 and self.fuse_raymarch and (self.max_deg_point - self.min_deg_point) == 10 and N == 128
+            if i_level > 0:
                 t_vals = ops.resample(t_vals, weights, u_rand=rb['u_rand'], padding=self.resample_padding)
-                rm = ops.raymarch(origins_s, dirs_s, radii, N, t_vals=t_vals, contract=self.contraction, ray_mult=bg_mult,
-                                  **common)
-            raw_rgb, raw_density, saved_bg = ops.mlp_fwd(bt, rm['features'], viewenc, variables.blob('MLP_0'), M=B, N=N,
-                                                         precision=prec, packed=variables.packed.get('MLP_0'),
-                                                         save=ctx is not None)
-            lvl_ctx = dict(feat_bg=rm['features'], saved_bg=saved_bg, obj=[]) if ctx is not None else None
+            rm_kw = dict(contract=self.contraction, ray_mult=bg_mult, min_deg=self.min_deg_point, max_deg=self.max_deg_point,
+                         ray_shape=self.ray_shape, integrate=not self.disable_integration)
+            if i_level == 0:
+                rm_kw.update(near=rays.near, far=rays.far, t_rand=rb['t_rand'])
+            else:
+                rm_kw.update(t_vals=t_vals)
+            if fuse:
+                # training keeps the tile image in HBM as well: the weight-gradient kernel reads it (job 0 and the skip layer)
+                feat_bg = torch.empty(B, 128 * 64, device=dev, dtype=torch.bfloat16) if ctx is not None else None
+                fz, t_vals, _keep = ops.fused_raymarch_args(origins_s, dirs_s, radii, N, **rm_kw)
+                raw_rgb, raw_density, saved_bg = ops.mlp_fwd(bt, feat_bg, viewenc, variables.blob('MLP_0'), M=B, N=N, precision=prec,
+                                                             packed=variables.packed.get('MLP_0'), save=ctx is not None, fused=fz)
+            else:
+                rm = ops.raymarch(origins_s, dirs_s, radii, N, bf16_tiles=bf16, **rm_kw)
+                t_vals, feat_bg = rm['t_vals'], rm['features']
+                raw_rgb, raw_density, saved_bg = ops.mlp_fwd(bt, feat_bg, viewenc, variables.blob('MLP_0'), M=B, N=N,
+                                                             precision=prec, packed=variables.packed.get('MLP_0'),
+                                                             save=ctx is not None)
+            lvl_ctx = dict(feat_bg=feat_bg, saved_bg=saved_bg, obj=[]) if ctx is not None else None
             if self.dynamics:
                 for k, (idx, cnt, m_host) in enumerate(obj_lists):
                     if m_host == 0:

@@ -207,18 +207,53 @@ def mlp_pack(topo, blob: torch.Tensor, packed: Optional[torch.Tensor] = None) ->
 
 
 def _mlp_args(topo, precision, M, N, features, cond, blob, packed, ray_index, count, accumulate, raw_rgb, raw_density, saved,
-              workspace):
+              workspace, fused=None):
     return L.MlpArgs(topo=topology(topo), precision=precision, M=M, N=N, features=ptr(features), cond=ptr(cond),
                      params=ptr(blob), packed=ptr(packed), ray_index=ptr(ray_index), count=ptr(count),
                      accumulate=int(accumulate), raw_rgb=ptr(raw_rgb), raw_density=ptr(raw_density), saved=ptr(saved),
-                     workspace=ptr(workspace), workspace_bytes=0 if workspace is None else workspace.numel() * workspace.element_size())
+                     workspace=ptr(workspace), workspace_bytes=0 if workspace is None else workspace.numel() * workspace.element_size(),
+                     fused_raymarch=None if fused is None else C.addressof(fused))
+
+
+def fused_raymarch_args(origins, dirs, radii, N: int, *, t_vals=None, near=None, far=None, t_rand=None, contract=False,
+                        weighted=False, alpha=0.0, min_deg=0, max_deg=10, ray_shape='cone', integrate=True, ray_mult=None):
+    """The arguments of `raymarch` as a struct for `mlp_fwd(..., fused=...)` (the tcgen05 MLP kernel generates its
+    own input tiles).  Returns (struct, t_vals, keepalive): t_vals is allocated here when it is to be sampled."""
+    if ray_shape not in ('cone', 'cylinder'):
+        raise AssertionError("ray_shape must be 'cone' or 'cylinder'")
+    origins, dirs = f32(origins), f32(dirs)
+    radii = f32(radii).reshape(-1)
+    B = origins.shape[0]
+    flags = 0
+    if t_vals is None:
+        flags |= L.RM_SAMPLE
+        t_vals = torch.empty(B, N + 1, device=_dev(origins))
+        near, far = f32(near).reshape(-1), f32(far).reshape(-1)
+        if t_rand is not None:
+            flags |= L.RM_RANDOMIZED
+            t_rand = f32(t_rand)
+    else:
+        t_vals = f32(t_vals)
+    if contract: flags |= L.RM_CONTRACT
+    if weighted: flags |= L.RM_WEIGHTED
+    if ray_shape == 'cylinder': flags |= L.RM_CYLINDER
+    if not integrate: flags |= L.RM_NO_INTEGRATE
+    flags |= L.RM_OUT_BF16_TILE
+    alpha_dev = alpha if torch.is_tensor(alpha) else None
+    keep = (origins, dirs, radii, near, far, t_rand, t_vals, ray_mult, alpha_dev)
+    a = L.RaymarchArgs(B=B, N=N, min_deg=min_deg, max_deg=max_deg, flags=flags, alpha=0.0 if alpha_dev is not None else float(alpha),
+                       origins=ptr(origins), dirs=ptr(dirs), radii=ptr(radii), near=ptr(near), far=ptr(far), t_rand=ptr(t_rand),
+                       t_vals=ptr(t_vals), ray_mult=ptr(ray_mult), ray_index=None, count=None, features=None, means=None,
+                       cov_diag=None, alpha_dev=ptr(alpha_dev))
+    return a, t_vals, keep
 
 
 def mlp_fwd(topo, features, cond, blob, *, M: int, N: int, precision=L.PREC_BF16, packed=None, ray_index=None, count=None,
-            accumulate=False, raw_rgb=None, raw_density=None, num_rays_out=None, save=False):
-    """Returns (raw_rgb[B,N,3], raw_density[B,N], saved-or-None)."""
+            accumulate=False, raw_rgb=None, raw_density=None, num_rays_out=None, save=False, fused=None):
+    """Returns (raw_rgb[B,N,3], raw_density[B,N], saved-or-None).  `fused` = the struct of `fused_raymarch_args`: the kernel
+    generates its input tiles itself (`features` may be None, or a tile buffer the generated tiles are also stored to)."""
     t = topology(topo)
-    dev = _dev(features)
+    dev = _dev(features if features is not None else cond)
     Bout = num_rays_out if num_rays_out is not None else M
     if raw_rgb is None:
         raw_rgb = torch.empty(Bout, N, 3, device=dev)
@@ -235,7 +270,7 @@ def mlp_fwd(topo, features, cond, blob, *, M: int, N: int, precision=L.PREC_BF16
         if save:      # training on the tensor-core path: every layer's bf16 activations as tile images
             saved = torch.empty(max(int(lib.durf_mlp_saved_bytes(C.byref(t), precision, M, N)), 16), device=dev, dtype=torch.uint8)
     a = _mlp_args(t, precision, M, N, features, f32(cond), f32(blob), packed, ray_index, count, accumulate, raw_rgb, raw_density,
-                  saved, ws)
+                  saved, ws, fused)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -192,6 +192,13 @@ typedef struct DurfMlpArgs {
                                backward call must pass the same buffer with the same M. */
   void* workspace;
   size_t workspace_bytes;
+  const struct DurfRaymarchArgs* fused_raymarch;
+                            /* [opt] BF16 only, SURVEY N1: the kernel GENERATES its input tiles (mip.sample_along_rays / cast_rays /
+                               mip360.new_space / integrated_pos_enc / weighted_ipe, mip.py:155-282, mip360.py:47-79) from these
+                               ray-march arguments instead of reading `features`: the 16 KB/ray-level tile image never touches HBM.
+                               B, N = 128, min_deg / max_deg (10 degrees) and the flags are taken from it; ray_index / count are this
+                               struct's; t_vals is written when DURF_RM_SAMPLE.  `features` may then be NULL; if it is not, the
+                               generated tiles are ALSO stored there (training: the weight-gradient kernel reads them). */
 } DurfMlpArgs;
 
 size_t durf_mlp_workspace_bytes(const DurfMlpTopology* topo, int32_t precision, int32_t M, int32_t N, int32_t training);
