@@ -32,7 +32,8 @@ namespace durf {
 constexpr int kInpBytes = 16384;      // input tile image: 128 rows x 64 bf16, K-major SWIZZLE_128B
 constexpr int kMaxG = 12;
 constexpr int kMaxStages = 8;
-constexpr int kMaxChunks = 48;
+constexpr int kMaxSteps = 112;
+constexpr int kMaxStageUses = 64;
 
 struct LayerSched {
   int n_halves;     // output columns / (W/2)
@@ -41,16 +42,33 @@ struct LayerSched {
   int kind;         // 0 relu->act, 1 relu->act + density head, 2 linear->act (bottleneck), 3 condition + rgb head + output
   int bias_off;     // offset (floats) of this layer's bias inside the parameter blob
   int last_inp_use; // 1 if no later layer of the tile reads the input-feature tile
+  int drain_sig;    // 1: the epilogue of half 1 signals "accumulator half 1 read out" (the next layer has two halves)
 };
 
-// One use of a weight-ring stage: the K blocks of one (layer, N-half) that come from the activation buffer, or the
-// single K block that comes from the input-feature tile (layer 0, skip layer).
-struct ChunkSched {
-  int g, nh;        // layer, N-half
-  int nkb;          // 16 KB weight blocks in this chunk
-  int inp;          // 1: A operand = input-feature tile (shared memory), 0: activation buffer (TMEM)
-  int first, last;  // first / last chunk of (g, nh): overwrite the accumulator / commit acc_full[nh]
-  int block0;       // index of the chunk's first 16 KB block inside the packed weight image
+// One K block (four K=16 tcgen05.mma of M=128, N=128) of a tile's schedule, in ISSUE ORDER.  A layer with two N-halves is
+// issued as  [h0: k0 k1] [h1: k0] [h0: k2 k3] [h1: k1] [h1: k2 k3]  (+ the input-tile block of layer 0 / the skip layer after
+// each half's last K block).  K blocks 0-1 of the A operand come from the epilogue of the previous layer's half 0 (long done),
+// blocks 2-3 from its half 1, which only STARTS when this layer starts: [h1: k0] gives the tensor core 4 more MMAs of
+// independent work before the first step that needs block 2, and half 0 still completes early (after 20 of the 32 MMAs), so
+// its epilogue finishes blocks 0-1 of the next layer well before that layer begins.  Every barrier is then complete >= 500
+// cycles before the step that needs it, more than the one-step lead of the software-pipelined probe (umma_kblock_conv); the
+// [h0: k0..k3][h1: k0..k3] order of round 1 left ~250 cycles for blocks 2-3 and lost ~230 cycles per layer.
+struct StepSched {
+  int8_t g, nh;         // layer, N-half
+  int8_t kb;            // K block of the layer's A operand (activation buffer), unused for inp
+  int8_t inp;           // 1: A operand = input-feature tile (shared memory), 0: activation buffer (TMEM)
+  int8_t acc0;          // 1: first K block of (g, nh): overwrite the accumulator
+  int8_t commit;        // 1: last K block of (g, nh): commit acc_full[nh]
+  int8_t stage_first;   // 1: first K block read from its ring stage
+  int8_t stage_last;    // 1: last K block read from its ring stage (release it)
+  int8_t slot;          // block index inside the ring stage
+  int8_t wait_a;        // 0..3: before this step, a_ready(k) must have completed (K block k of the A operand is in TMEM);
+                        // 4: the previous layer's epilogue has read accumulator half 1 out (this step overwrites it); -1: nothing
+  int8_t pad[2];
+};
+// One use of a weight-ring stage: `nkb` consecutive 16 KB blocks of the packed image starting at `block0`.
+struct StageUse {
+  int16_t block0, nkb;
 };
 
 struct TcParams {
@@ -71,7 +89,8 @@ struct TcParams {
   int G;                     // GEMM layers per tile: depth + 2
   int depth;
   int cond_dim;
-  int n_chunks;              // ring-stage uses per tile
+  int n_steps;               // K-block steps per tile
+  int n_uses;                // ring-stage uses per tile
   int off_wden, off_bden, off_wrgb, off_brgb, off_wview;
   int trace;                 // DURF_TC_TRACE=1: block 0 prints where its MMA thread and one epilogue thread spent their cycles
   // N1: the input tile is GENERATED inside the kernel by warps 2-3 (fenceposts -> conical-frustum Gaussian ->
@@ -91,8 +110,49 @@ struct TcParams {
   float* g_t_vals;           // [B,129]: written when DURF_RM_SAMPLE, else read
   uint8_t* feat_out;         // [opt] the generated tiles are also stored here (training: wgrad reads them)
   LayerSched sched[kMaxG];
-  ChunkSched chunks[kMaxChunks];
+  StepSched steps[kMaxSteps];   // host side (pack kernel, debugging)
+  uint32_t step_w[kMaxSteps];   // the same, one packed word per step: what the MMA issuer reads (see step_word)
+  StageUse uses[kMaxStageUses];
 };
+
+// The K-block steps of ONE layer in issue order, as a compile-time table: the host builds the packed weight image and the
+// ring-stage list from it (build_sched), the MMA issuer unrolls it (issue_layer) - so that every operand of a tcgen05
+// instruction is a compile-time function of a few loop-carried uniform values.  (A fully table-driven issuer, one decoded
+// descriptor per step, was measured at 580 cycles per 4 MMAs instead of 316: the issuing thread has no latency hiding, and
+// a ~250-cycle dependent decode chain per step is not hidden behind 4 MMAs.)
+struct LayerSteps {
+  int n;
+  int8_t nh[12], kb[12], inp[12], acc0[12], commit[12], wait[12];
+};
+__host__ __device__ constexpr LayerSteps layer_steps(int nh, int kbs, bool inp, bool drained_wait) {
+  LayerSteps L{};
+  auto add = [&](int h, int kb, bool is_inp, bool first, bool last, int wait) {
+    L.nh[L.n] = (int8_t)h; L.kb[L.n] = (int8_t)kb; L.inp[L.n] = is_inp ? 1 : 0; L.acc0[L.n] = first ? 1 : 0;
+    L.commit[L.n] = last ? 1 : 0; L.wait[L.n] = (int8_t)wait; ++L.n;
+  };
+  if (nh == 2 && kbs == 4) {
+    add(0, 0, false, true, false, 0); add(0, 1, false, false, false, 1);
+    add(1, 0, false, true, false, drained_wait ? 4 : -1);
+    add(0, 2, false, false, false, 2); add(0, 3, false, false, !inp, 3);
+    if (inp) add(0, 0, true, false, true, -1);
+    add(1, 1, false, false, false, -1); add(1, 2, false, false, false, -1); add(1, 3, false, false, !inp, -1);
+    if (inp) add(1, 0, true, false, true, -1);
+  } else {
+    // one N-half (width 128, condition layer) or no activation input (layer 0): half after half, K blocks in order
+    for (int h = 0; h < nh; ++h) {
+      for (int kb = 0; kb < kbs; ++kb) add(h, kb, false, kb == 0, kb == kbs - 1 && !inp, h == 0 ? kb : -1);
+      if (inp) add(h, 0, true, kbs == 0, true, -1);
+    }
+  }
+  return L;
+}
+
+// bits: g 0-3 | nh 4 | kb 5-6 | inp 7 | acc0 8 | commit 9 | stage_first 10 | stage_last 11 | slot 12-13 | wait_a + 1 14-16
+__host__ __device__ __forceinline__ uint32_t step_word(const StepSched& sp) {
+  return (uint32_t)sp.g | ((uint32_t)sp.nh << 4) | ((uint32_t)sp.kb << 5) | ((uint32_t)sp.inp << 7) | ((uint32_t)sp.acc0 << 8) |
+         ((uint32_t)sp.commit << 9) | ((uint32_t)sp.stage_first << 10) | ((uint32_t)sp.stage_last << 11) | ((uint32_t)sp.slot << 12) |
+         ((uint32_t)(sp.wait_a + 1) << 14);
+}
 
 // Epilogue arithmetic of one 32-column group, specialised per layer kind so that the unrolled body has no branches:
 // KIND 0: relu(acc + bias) -> bf16; KIND 1: the same + fp32 partial dot product with the density head; KIND 2: linear.
@@ -128,7 +188,12 @@ struct TcCfg {
   // 64 KB to the per-warp staging of the activation stores, which leaves 128 KB: two whole chunks would mean a chunk's
   // weights can only be requested when the chunk before it has completed (measured: -17 % MMA rate), so the ring is cut into
   // four 32 KB stages of two K blocks, each released by the MMA issuer's commit as soon as its own MMAs are done.
-  static constexpr int SKB = (SAVE && W == 256) ? 2 : KB; // K blocks per ring stage
+  // Weight ring: a stage holds up to SKB consecutive K blocks of the issue order (never across a layer boundary).  Inference:
+  // 64 KB stages at W = 256 (two per layer, three in the ring), i.e. two stage releases and two weight probes per layer - every
+  // tcgen05.commit costs the issuing thread ~190 cycles and every barrier probe ~140, and that thread has only the ~2500
+  // cycles of a layer's MMAs to spend.  Training (SAVE) gives 64 KB to the per-warp staging of the activation stores, which
+  // leaves 128 KB: four 32 KB stages.
+  static constexpr int SKB = (W == 256 && !SAVE) ? 4 : 2;
   static constexpr int STAGE_BYTES = SKB * kBlockBytes;
   static constexpr int STAGES = SAVE ? 4 : ((W == 256) ? 3 : 6);
   static constexpr int TMEM_COLS = 2 * W;                 // W accumulator columns + 2 x W/2 activation columns
@@ -150,6 +215,56 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;     // + alignment slack
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
+
+// State the MMA issuer carries from step to step (all warp-uniform).
+struct IssueState {
+  uint32_t stage, phase;   // weight-ring position
+  uint32_t ar_bits;        // bit k: parity of a_ready(k) (k = 4: "accumulator half 1 drained")
+};
+
+// All K-block steps of one layer, unrolled from the compile-time table layer_steps(NH, KBS, INP, DRAINED).  Every step
+// issues its four MMAs and, inside the same asm block, probes / waits for what the NEXT step needs (umma_kblock_conv);
+// for the layer's last step that is the first step of the next layer: its weights (need_w_after) and a_ready(0)
+// (need_a0_after).  `blk0` = index of the layer's first K block inside its ring stage sequence is always 0: stages never
+// cross a layer boundary.
+template <class C, int W, int NH, int KBS, bool INP, bool DRAINED>
+__device__ __forceinline__ void issue_layer(IssueState& st, uint32_t sbase, uint32_t bar0, uint32_t tmem_u, uint32_t inp_lo, int g,
+                                            uint32_t need_a0_after, uint32_t need_w_after, uint32_t rel_mask) {
+  constexpr LayerSteps LS = layer_steps(NH, KBS, INP, DRAINED);
+  constexpr uint32_t idesc = umma_idesc(128, 128);
+  constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);     // SBO | version | SWIZZLE_128B
+  auto bar_full = [&](uint32_t s_) { return bar0 + 8 * s_; };
+  auto bar_empty = [&](uint32_t s_) { return bar0 + 8 * (kMaxStages + s_); };
+  auto bar_acc_full = [&](int h) { return bar0 + 8 * (2 * kMaxStages + 2 + h); };
+  auto bar_a_ready = [&](int kb) { return bar0 + 8 * (2 * kMaxStages + 4 + kb); };
+  const uint32_t a_buf = tmem_u + C::ACT_COL + (g & 1) * (W / 2);       // written by the epilogue of layer g-1
+#pragma unroll
+  for (int i = 0; i < LS.n; ++i) {
+    constexpr int SKB = C::SKB;
+    const int slot = i % SKB;
+    const bool stage_last = (slot == SKB - 1) || (i == LS.n - 1);
+    const bool last = i == LS.n - 1;
+    if (LS.wait[i] >= 0) st.ar_bits ^= 1u << LS.wait[i];     // this step's a_ready was waited for inside the previous step
+    tc_fence_after();
+    // what the next step needs
+    const int nwait = last ? 0 : (LS.wait[i + 1] >= 0 ? LS.wait[i + 1] : 0);
+    const uint32_t need_a = last ? need_a0_after : (LS.wait[i + 1] >= 0 ? 1u : 0u);
+    const uint32_t need_w = last ? need_w_after : (stage_last ? 1u : 0u);
+    const uint32_t next_stage = (st.stage + 1 == (uint32_t)C::STAGES) ? 0 : st.stage + 1;
+    const uint32_t next_phase = (st.stage + 1 == (uint32_t)C::STAGES) ? st.phase ^ 1 : st.phase;
+    const uint32_t d_addr = tmem_u + C::ACC_COL + LS.nh[i] * 128;
+    const uint32_t b_lo = (((sbase + C::OFF_RING + st.stage * C::STAGE_BYTES + slot * kBlockBytes) & 0x3FFFF) >> 4) | (1u << 16);
+    if (!LS.inp[i])
+      umma_kblock_conv<true>(d_addr, a_buf + LS.kb[i] * 32, b_lo, desc_hi, idesc, LS.acc0[i] ? 0u : 1u,
+                             bar_a_ready(nwait), (st.ar_bits >> nwait) & 1u, need_a, bar_full(next_stage), next_phase, need_w,
+                             bar_acc_full(LS.nh[i]), LS.commit[i] ? 1u : 0u, bar_empty(st.stage), stage_last ? 1u : 0u, rel_mask);
+    else
+      umma_kblock_conv<false>(d_addr, inp_lo, b_lo, desc_hi, idesc, LS.acc0[i] ? 0u : 1u,
+                              bar_a_ready(nwait), (st.ar_bits >> nwait) & 1u, need_a, bar_full(next_stage), next_phase, need_w,
+                              bar_acc_full(LS.nh[i]), LS.commit[i] ? 1u : 0u, bar_empty(st.stage), stage_last ? 1u : 0u, rel_mask);
+    if (stage_last) { st.stage = next_stage; st.phase = next_phase; }
+  }
+}
 
 template <int W, bool SAVE>
 __global__ void __launch_bounds__(384, 1)
@@ -176,15 +291,15 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
   auto bar_empty = [&](int s) { return bar0 + 8 * (kMaxStages + s); };
   const uint32_t bar_inp_full = bar0 + 8 * (2 * kMaxStages), bar_inp_empty = bar0 + 8 * (2 * kMaxStages + 1);
   auto bar_acc_full = [&](int h) { return bar0 + 8 * (2 * kMaxStages + 2 + h); };
-  auto bar_a_ready = [&](int kb) { return bar0 + 8 * (2 * kMaxStages + 4 + kb); };   // one per 64-column K block of the next layer's A
-  static_assert(32 + 8 * (2 * kMaxStages + 8) + 64 <= C::MISC_BYTES, "barrier area + BARF weights");
-  float* s_barf = reinterpret_cast<float*>(smem + C::OFF_MISC + 32 + 8 * (2 * kMaxStages + 8));     // [16] (weighted IPE)
+  auto bar_a_ready = [&](int kb) { return bar0 + 8 * (2 * kMaxStages + 4 + kb); };   // 0..3: one per 64-column K block of the next layer's A; 4: accumulator half 1 drained
+  static_assert(32 + 8 * (2 * kMaxStages + 9) + 64 <= C::MISC_BYTES, "barrier area + BARF weights");
+  float* s_barf = reinterpret_cast<float*>(smem + C::OFF_MISC + 32 + 8 * (2 * kMaxStages + 9));     // [16] (weighted IPE)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), nct); }
     mbar_init(bar_inp_full, p.gen ? 2 : 1); mbar_init(bar_inp_empty, 1);   // generated tiles: one arrival per generator warp
     for (int h = 0; h < 2; ++h) mbar_init(bar_acc_full(h), 1);
-    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_a_ready(kb), 8);   // one arrival per epilogue warp
+    for (int kb = 0; kb < 5; ++kb) mbar_init(bar_a_ready(kb), 8);   // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -221,22 +336,21 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; more(tile); tile += gridDim.x) {
-        for (int c = 0; c < p.n_chunks; ++c) {
-          const ChunkSched ck = p.chunks[c];
-          for (int kb0 = 0; kb0 < ck.nkb; kb0 += C::SKB) {   // the chunk's K blocks are contiguous in the packed image
-            const uint32_t bytes = (uint32_t)min(C::SKB, ck.nkb - kb0) * kBlockBytes;
-            mbar_wait(bar_empty(stage), phase ^ 1);          // released by the MMA issuer of every CTA of the cluster
-            mbar_arrive_expect_tx(bar_full(stage), bytes);
-            const uint32_t dst = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
-            const uint8_t* src = p.packed + (size_t)(ck.block0 + kb0) * kBlockBytes;
-            if (nct == 1) {
-              bulk_g2s(dst, src, bytes, bar_full(stage));
-            } else {
-              const uint32_t part = bytes / nct;
-              bulk_g2s_multicast(dst + crank * part, src + crank * part, part, bar_full(stage), (uint16_t)((1u << nct) - 1));
-            }
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        for (int u = 0; u < p.n_uses; ++u) {
+          const StageUse su = p.uses[u];
+          const uint32_t bytes = (uint32_t)su.nkb * kBlockBytes;
+          mbar_wait(bar_empty(stage), phase ^ 1);          // released by the MMA issuer of every CTA of the cluster
+          mbar_arrive_expect_tx(bar_full(stage), bytes);
+          const uint32_t dst = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
+          const uint8_t* src = p.packed + (size_t)su.block0 * kBlockBytes;
+          if (nct == 1) {
+            bulk_g2s(dst, src, bytes, bar_full(stage));
+          } else if ((uint32_t)u % nct == crank) {
+            // the CTAs of a pair take turns: one fetches the WHOLE stage and multicasts it to both (a 32 KB copy streams at
+            // ~120 B/cycle/SM, two 16 KB halves at ~67: profiles/r01_ubench_stream.log); every CTA armed its own barrier above
+            bulk_g2s_multicast(dst, src, bytes, bar_full(stage), (uint16_t)((1u << nct) - 1));
           }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -244,74 +358,46 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp walks the schedule (uniform control flow), one elected lane issues =====
     {
-      constexpr uint32_t idesc = umma_idesc(128, 128);
-      constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);     // SBO | version | SWIZZLE_128B
-      uint32_t stage = 0, phase = 0;
-      uint32_t ar_par[4] = {0, 0, 0, 0}, inp_par = 0;
+      IssueState st{0u, 0u, 0u};
+      uint32_t inp_par = 0;
       int it = 0;
       const bool tr = p.trace && blockIdx.x == 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       long long t_start = 0, t_begin = clock64(), tq = 0;
       const uint32_t inp_lo = ((sbase + C::OFF_INP) & 0x3FFFF) >> 4 | (1u << 16);
+      const uint32_t rel_mask = nct > 1 ? (1u << nct) - 1 : 0u;
       // Every K block of MMAs waits - inside umma_kblock_conv, after its MMAs are queued - for the barriers of the NEXT
       // K block, so the thread itself never sits in a wait with an empty tensor queue behind it.  Only the first weights
       // and the per-tile start conditions are waited for up front.
       if (more(blockIdx.x)) mbar_wait(bar_full(0), 0);
       for (int tile = blockIdx.x; more(tile); tile += gridDim.x, ++it) {
         const bool more_tiles = more(tile + (int)gridDim.x);
-        for (int c = 0; c < p.n_chunks; ++c) {
-          const ChunkSched ck = p.chunks[c];
-          const uint32_t d_addr = tmem_u + C::ACC_COL + ck.nh * 128;
-          if (c == 0) {
-            if (tr) tq = clock64();
-            mbar_wait(bar_inp_full, inp_par); inp_par ^= 1;
-            if (it > 0) {    // accumulators of the previous tile's last layer must have been drained
-              mbar_wait(bar_a_ready(0), ar_par[0]); ar_par[0] ^= 1;
-              if (halves_last > 1) { mbar_wait(bar_a_ready(2), ar_par[2]); ar_par[2] ^= 1; }
-            }
-            if (tr) t_start += clock64() - tq;
-          }
-          tc_fence_after();      // this chunk's weights (and its first K block) were waited for by the previous K block
-          // what the first K block of the next chunk needs: its weights, and K block 0 of its A operand if it opens a layer
-          const bool last_chunk = c + 1 == p.n_chunks;
-          const uint32_t need_w = (!last_chunk || more_tiles) ? 1u : 0u;
-          const uint32_t need_a0 = (!last_chunk && p.chunks[c + 1].nh == 0 && !p.chunks[c + 1].inp) ? 1u : 0u;
-          const uint32_t rel_mask = nct > 1 ? (1u << nct) - 1 : 0u;
-          if (!ck.inp) {
-            const uint32_t a_buf = tmem_u + C::ACT_COL + (ck.g & 1) * (W / 2);     // written by the epilogue of layer g-1
-#pragma unroll
-            for (int kb = 0; kb < C::KB; ++kb) {
-              if (kb < ck.nkb) {
-                if (ck.nh == 0) { ar_par[kb] ^= 1; tc_fence_after(); }   // K block kb of the A operand (previous layer's epilogue) is there
-                const uint32_t acc0 = (ck.first && kb == 0) ? 0u : 1u;
-                const uint32_t b_lo = (((sbase + C::OFF_RING + stage * C::STAGE_BYTES + (kb % C::SKB) * kBlockBytes) & 0x3FFFF) >> 4) | (1u << 16);
-                const bool chunk_end = kb + 1 == ck.nkb;
-                const bool stage_end = chunk_end || (kb % C::SKB) == C::SKB - 1;      // last K block read from this ring stage
-                const uint32_t next_stage = (stage + 1 == C::STAGES) ? 0 : stage + 1;
-                const uint32_t next_phase = (stage + 1 == C::STAGES) ? phase ^ 1 : phase;
-                if (!chunk_end)
-                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo, desc_hi, idesc, acc0,
-                                         bar_a_ready((kb + 1) & 3), ar_par[(kb + 1) & 3], ck.nh == 0 ? 1u : 0u,
-                                         bar_full(next_stage), next_phase, stage_end ? 1u : 0u, bar_acc_full(ck.nh), 0u,
-                                         bar_empty(stage), stage_end ? 1u : 0u, rel_mask);
-                else
-                  umma_kblock_conv<true>(d_addr, a_buf + kb * 32, b_lo, desc_hi, idesc, acc0,
-                                         bar_a_ready(0), ar_par[0], need_a0, bar_full(next_stage), next_phase, need_w,
-                                         bar_acc_full(ck.nh), ck.last ? 1u : 0u, bar_empty(stage), 1u, rel_mask);
-                if (stage_end) { stage = next_stage; phase = next_phase; }
-              }
-            }
+        if (tr) tq = clock64();
+        mbar_wait(bar_inp_full, inp_par); inp_par ^= 1;
+        if (it > 0) {    // accumulators of the previous tile's last layer must have been drained
+          mbar_wait(bar_a_ready(0), st.ar_bits & 1u); st.ar_bits ^= 1u;
+          if (halves_last > 1) { mbar_wait(bar_a_ready(2), (st.ar_bits >> 2) & 1u); st.ar_bits ^= 4u; }
+        }
+        if (tr) t_start += clock64() - tq;
+        for (int g = 0; g < p.G; ++g) {
+          const LayerSched& Ls = p.sched[g];
+          const bool last_layer = g + 1 == p.G;
+          // the first step of the next layer: a_ready(0) unless it reads the input tile (layer 0 of the next tile, whose
+          // start conditions are waited for explicitly above); its weights unless this was the last tile
+          const uint32_t na0 = last_layer ? 0u : 1u;
+          const uint32_t nw = (!last_layer || more_tiles) ? 1u : 0u;
+          const int kbs = Ls.n_act_kb;
+          const bool inp = Ls.uses_inp != 0;
+          if (W == 256) {
+            if (kbs == 0) issue_layer<C, W, 2, 0, true, false>(st, sbase, bar0, tmem_u, inp_lo, g, na0, nw, rel_mask);
+            else if (Ls.n_halves == 2 && !inp) issue_layer<C, W, 2, 4, false, true>(st, sbase, bar0, tmem_u, inp_lo, g, na0, nw, rel_mask);
+            else if (Ls.n_halves == 2) issue_layer<C, W, 2, 4, true, true>(st, sbase, bar0, tmem_u, inp_lo, g, na0, nw, rel_mask);
+            else issue_layer<C, W, 1, 4, false, false>(st, sbase, bar0, tmem_u, inp_lo, g, na0, nw, rel_mask);
           } else {
-            const uint32_t b_lo = (((sbase + C::OFF_RING + stage * C::STAGE_BYTES) & 0x3FFFF) >> 4) | (1u << 16);
-            const uint32_t next_stage = (stage + 1 == C::STAGES) ? 0 : stage + 1;
-            const uint32_t next_phase = (stage + 1 == C::STAGES) ? phase ^ 1 : phase;
-            umma_kblock_conv<false>(d_addr, inp_lo, b_lo, desc_hi, idesc, ck.first ? 0u : 1u,
-                                    bar_a_ready(0), ar_par[0], need_a0, bar_full(next_stage), next_phase, need_w,
-                                    bar_acc_full(ck.nh), ck.last ? 1u : 0u, bar_empty(stage), 1u, rel_mask);
-            stage = next_stage; phase = next_phase;
+            if (kbs == 0) issue_layer<C, W, 1, 0, true, false>(st, sbase, bar0, tmem_u, inp_lo, g, na0, nw, rel_mask);
+            else if (!inp) issue_layer<C, W, 1, 2, false, false>(st, sbase, bar0, tmem_u, inp_lo, g, na0, nw, rel_mask);
+            else issue_layer<C, W, 1, 2, true, false>(st, sbase, bar0, tmem_u, inp_lo, g, na0, nw, rel_mask);
           }
-          // (the commits - ring stage release, and the accumulator barrier of a layer half's last chunk - are issued inside
-          // umma_kblock_conv, between the MMAs and the wait for the next K block's barriers)
         }
       }
       if (tr && lane == 0) printf("durf mlp_tc trace: MMA thread: %d tiles, total %lld cyc; tile start (features, drained accumulators) %lld\n",
@@ -520,6 +606,14 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
               tmem_ld_pin(v[i]);
               if (tr && i == 1) e_ld1 += clock64() - tq1;
               if (i + 1 < NG) tmem_ld32_issue(t_lane + C::ACC_COL + gcol(i + 1), v[i + 1]);
+              if (i == 0 && h == 1 && L.drain_sig) {
+                // accumulator half 1 is in registers: the next layer's [h1: k0] (issued before anything that depends on this
+                // epilogue's output) may overwrite it.  Off the critical path: every consumer of this half's output has slack.
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_a_ready(4));
+              }
               if (tr && i == 0) { e_ld += clock64() - eq; eq = clock64(); }
               if (tr) tq1 = clock64();
               const uint32_t wden_addr = sbase + C::OFF_WDEN + cg * 4;
@@ -683,7 +777,7 @@ static bool tc_supported(const DurfMlpTopology& t) {
 
 // Builds the per-layer schedule and the flat list of ring-stage uses shared by the pack kernel and the MLP kernel.
 // Returns the number of 16 KB weight blocks.
-static int build_sched(const DurfMlpTopology& t, TcParams& P) {
+static int build_sched(const DurfMlpTopology& t, TcParams& P, int skb = 2) {
   MlpLayout L(t);
   const int KB = t.width / 64;
   int last_inp = 0;
@@ -708,23 +802,36 @@ static int build_sched(const DurfMlpTopology& t, TcParams& P) {
     s.last_inp_use = 0;
   }
   P.sched[last_inp].last_inp_use = 1;
-  int blocks = 0, nc = 0;
+  // Issue order (see StepSched).  Every group of <= 2 K blocks of one N-half is one ring-stage use; the packed image stores
+  // the blocks in exactly this order.
+  int blocks = 0, ns = 0, nu = 0;
+  for (int g = 0; g < P.G; ++g)
+    P.sched[g].drain_sig = (g + 1 < P.G && P.sched[g].n_halves == 2 && P.sched[g + 1].n_halves == 2 && P.sched[g + 1].n_act_kb == 4) ? 1 : 0;
   for (int g = 0; g < P.G; ++g) {
     const LayerSched& s = P.sched[g];
-    for (int nh = 0; nh < s.n_halves; ++nh) {
-      const int parts = (s.n_act_kb > 0 ? 1 : 0) + s.uses_inp;
-      int part = 0;
-      if (s.n_act_kb > 0) {
-        P.chunks[nc++] = ChunkSched{g, nh, s.n_act_kb, 0, part == 0, part == parts - 1, blocks};
-        blocks += s.n_act_kb; ++part;
-      }
-      if (s.uses_inp) {
-        P.chunks[nc++] = ChunkSched{g, nh, 1, 1, part == 0, part == parts - 1, blocks};
-        blocks += 1; ++part;
-      }
+    const bool drained = g >= 1 && P.sched[g - 1].drain_sig;
+    const LayerSteps LS = layer_steps(s.n_halves, s.n_act_kb, s.uses_inp != 0, drained);
+    for (int i = 0; i < LS.n; ++i) {
+      StepSched& sp = P.steps[ns++];
+      sp.g = (int8_t)g; sp.nh = LS.nh[i]; sp.kb = LS.kb[i]; sp.inp = LS.inp[i]; sp.acc0 = LS.acc0[i]; sp.commit = LS.commit[i];
+      sp.stage_first = sp.stage_last = sp.slot = 0; sp.wait_a = LS.wait[i]; sp.pad[0] = sp.pad[1] = 0;
     }
+    blocks += LS.n;
   }
-  P.n_chunks = nc;
+  // ring-stage uses: up to `skb` consecutive K blocks of the issue order, never across a layer boundary
+  for (int c = 0; c < ns;) {
+    int n = 1;
+    while (n < skb && c + n < ns && P.steps[c + n].g == P.steps[c].g) ++n;
+    P.uses[nu].block0 = (int16_t)c; P.uses[nu].nkb = (int16_t)n; ++nu;
+    for (int i = 0; i < n; ++i) {
+      P.steps[c + i].slot = (int8_t)i;
+      P.steps[c + i].stage_first = i == 0 ? 1 : 0;
+      P.steps[c + i].stage_last = i == n - 1 ? 1 : 0;
+    }
+    c += n;
+  }
+  for (int c = 0; c < ns; ++c) P.step_w[c] = step_word(P.steps[c]);
+  P.n_steps = ns; P.n_uses = nu;
   P.off_wden = (int)L.w_off[t.depth]; P.off_bden = (int)L.b_off[t.depth];
   P.off_wrgb = (int)L.w_off[t.depth + 3]; P.off_brgb = (int)L.b_off[t.depth + 3];
   P.off_wview = (int)L.w_off[t.depth + 2] + t.width * t.cond_width;
@@ -742,24 +849,22 @@ int mlp_tc_pack(cudaStream_t st, const DurfMlpTopology& t, const float* params, 
                "durf_mlp_pack_weights: tensor-core path needs width 128/256, cond_width 128, in_dim <= 64, depth <= 9");
   TcParams P;
   const int blocks = build_sched(t, P);
-  DURF_REQUIRE(blocks <= kMaxBlocks && P.n_chunks <= kMaxChunks, DURF_E_UNSUPPORTED, "durf_mlp_pack_weights: too many weight blocks (%d)", blocks);
+  DURF_REQUIRE(blocks <= kMaxBlocks && P.n_steps <= kMaxSteps && P.n_uses <= kMaxStageUses, DURF_E_UNSUPPORTED,
+               "durf_mlp_pack_weights: too many weight blocks (%d)", blocks);
   MlpLayout L(t);
   PackParams pp;
   pp.params = params; pp.packed = (uint8_t*)packed; pp.n_blocks = blocks;
-  int c = 0;
-  for (int g = 0; g < P.G; ++g) {
-    const LayerSched& s = P.sched[g];
+  for (int c = 0; c < P.n_steps; ++c) {          // block c of the image = K block of step c (same order as the ring-stage uses)
+    const StepSched& sp = P.steps[c];
+    const int g = sp.g;
     const int layer = (g < t.depth) ? g : (g == t.depth ? t.depth + 1 : t.depth + 2);
     const int n_out = L.out_dim[layer];
-    for (int nh = 0; nh < s.n_halves; ++nh)
-      for (int kc = 0; kc < s.n_act_kb + s.uses_inp; ++kc, ++c) {     // same order as build_sched's block numbering
-        pp.w_off[c] = (int)L.w_off[layer];
-        pp.ld[c] = n_out;
-        pp.n_first[c] = nh * 128;
-        pp.n_avail[c] = n_out - nh * 128 < 128 ? n_out - nh * 128 : 128;
-        if (kc < s.n_act_kb) { pp.k_first[c] = kc * 64; pp.k_avail[c] = 64; }
-        else { pp.k_first[c] = (g == 0) ? 0 : t.width; pp.k_avail[c] = t.in_dim; }   // input-feature block (skip rows follow the trunk rows)
-      }
+    pp.w_off[c] = (int)L.w_off[layer];
+    pp.ld[c] = n_out;
+    pp.n_first[c] = sp.nh * 128;
+    pp.n_avail[c] = n_out - sp.nh * 128 < 128 ? n_out - sp.nh * 128 : 128;
+    if (!sp.inp) { pp.k_first[c] = sp.kb * 64; pp.k_avail[c] = 64; }
+    else { pp.k_first[c] = (g == 0) ? 0 : t.width; pp.k_avail[c] = t.in_dim; }   // input-feature block (skip rows follow the trunk rows)
   }
   const int64_t total = (int64_t)blocks * 1024;
   pack_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(pp);
@@ -793,7 +898,7 @@ int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a) {
   DURF_REQUIRE(a.workspace && a.workspace_bytes >= need, DURF_E_WORKSPACE, "durf_mlp_fwd(bf16): workspace %zu < %zu bytes",
                a.workspace_bytes, need);
   TcParams P;
-  build_sched(t, P);
+  build_sched(t, P, (t.width == 256 && a.saved == nullptr) ? 4 : 2);      // = TcCfg<W, SAVE>::SKB
   P.vbias = (const float*)a.workspace;
   P.saved = (uint8_t*)a.saved;
   P.saved_blocks_per_tile = mlp_tc_saved_blocks(t);

@@ -195,16 +195,22 @@ class MipNerfModel:
                             lvl_ctx['obj'].append(None)
                         continue
                     rows = m_host if m_host is not None else (B if self.max_obj_rays is None else min(B, self.max_obj_rays))
-                    rmo = ops.raymarch(origins_s, dirs_s, radii, N, t_vals=t_vals, weighted=True, alpha=alpha, ray_index=idx,
-                                       count=None if m_host is not None else cnt, rows=rows,
-                                       **dict(common, bf16_tiles=obj_prec == L.PREC_BF16))
-                    _, _, saved_o = ops.mlp_fwd(ot, rmo['features'], viewenc, variables.blob(f'BoxMLP_{k}'), M=rows, N=N,
+                    dev_cnt = None if m_host is not None else cnt
+                    if fuse and obj_prec == L.PREC_BF16:
+                        feat_o = torch.empty(rows, 128 * 64, device=dev, dtype=torch.bfloat16) if ctx is not None else None
+                        fzo, _, _keep_o = ops.fused_raymarch_args(origins_s, dirs_s, radii, N, t_vals=t_vals, weighted=True, alpha=alpha,
+                                                                  min_deg=self.min_deg_point, max_deg=self.max_deg_point,
+                                                                  ray_shape=self.ray_shape, integrate=not self.disable_integration)
+                    else:
+                        fzo = None
+                        feat_o = ops.raymarch(origins_s, dirs_s, radii, N, t_vals=t_vals, weighted=True, alpha=alpha, ray_index=idx,
+                                              count=dev_cnt, rows=rows, **dict(common, bf16_tiles=obj_prec == L.PREC_BF16))['features']
+                    _, _, saved_o = ops.mlp_fwd(ot, feat_o, viewenc, variables.blob(f'BoxMLP_{k}'), M=rows, N=N,
                                                 precision=obj_prec, packed=variables.packed.get(f'BoxMLP_{k}'), ray_index=idx,
-                                                count=None if m_host is not None else cnt, accumulate=True, raw_rgb=raw_rgb,
-                                                raw_density=raw_density, save=ctx is not None)
+                                                count=dev_cnt, accumulate=True, raw_rgb=raw_rgb, raw_density=raw_density,
+                                                save=ctx is not None, fused=fzo)
                     if lvl_ctx is not None:
-                        lvl_ctx['obj'].append(dict(feat=rmo['features'], saved=saved_o, rows=rows,
-                                                   count=None if m_host is not None else cnt))
+                        lvl_ctx['obj'].append(dict(feat=feat_o, saved=saved_o, rows=rows, count=dev_cnt))
             if randomized and self.density_noise > 0:
                 raw_density = raw_density + self.density_noise * rb['density_noise'][i_level]   # obbpose_model.py:237-240
             comp = ops.composite(raw_rgb, raw_density, t_vals, dirs_s, white_bkgd=white_bkgd, rand_bkgd=rand_bkgd,
