@@ -609,11 +609,11 @@ def main():
     flops = float(n_rays) * N_SAMPLES * 2 * MLP_FLOP_PER_SAMPLE * steps
     ach = flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
     traffic = None                                        # DRAM bytes per launch from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "r01_mlp_fwd_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_mlp_fwd_traffic.json")
     if os.path.exists(tpath) and n_mlp > 0:
         traffic = json.load(open(tpath))["dram_bytes_per_tile"] * (float(n_rays) * 2 * steps / n_mlp)
-    roof = dict(bound="tensor", kernel="mlp_tc_fwd_kernel<256>", achieved=ach, peak=peaks["tf_sustained"], unit="TFLOP/s",
-                frac=ach / peaks["tf_sustained"], traffic=traffic, traffic_unit="bytes per launch (ncu dram read+write, profiles/r01_mlp_fwd_traffic.json)",
+    roof = dict(bound="tensor", kernel="mlp_tc_fwd_kernel<256> (ray-march fused in)", achieved=ach, peak=peaks["tf_sustained"], unit="TFLOP/s",
+                frac=ach / peaks["tf_sustained"], traffic=traffic, traffic_unit="bytes per launch (ncu dram read+write, profiles/r02_mlp_fwd_traffic.json)",
                 flops_per_launch=flops / max(n_mlp, 1), peak_source=peaks["src"] + " (sustained bf16 cuBLAS)",
                 launches=n_mlp, avg_launch_ms=mlp_ms / max(n_mlp, 1), share_of_step=mlp_ms / (ms_resident * steps))
     line = dict(metric="rays/sec (render, 2x128 samples)", value=value, unit="rays/s", n_gpus=world, steps=steps, warmup=warmup,
@@ -621,7 +621,8 @@ def main():
                 dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
                 config=dict(workload=WORKLOAD_C2, rays_per_step_per_gpu=n_rays, chunk=chunk, mlp="8x256 + cond 128, random init",
                             sharding="one camera frame per GPU, no collective",
-                            l2="per-chunk working set (1 GB bf16 feature tiles) exceeds the 126 MB L2; no explicit flush"),
+                            l2="every chunk streams 65,536 new rays (3 MB of rays + 34 MB of t_vals + 134 MB of raw outputs + 34 MB of "
+                               "view bias per level > the 126 MB L2 over a frame of 38 chunks); no explicit flush"),
                 clocks=dict(sm_mhz=clocks["sm_mhz"], sm_max_mhz=clocks["sm_max_mhz"], reasons=clocks["reasons"],
                             samples=clocks["samples"], power_w_max=clocks.get("power_w_max")),
                 e2e=dict(value=e2e_v, unit="rays/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e,
