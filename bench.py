@@ -205,9 +205,13 @@ def train_bench(dev, rank, world, steps, warmup, precision, pose=False, global_b
     K, N = 2, N_SAMPLES
     strong = global_batch is not None
     B_all = global_batch if strong else 16384
-    rng = np.random.default_rng(S.SEED + 7 + (0 if strong else rank))     # strong: the same scene and batch on every rank
-    rays_np, c2w = S.random_rays(rng, B_all, far=40.0)
-    centers, ext_np = S.boxes_in_view(rng, c2w, K)
+    # ONE scene (camera, boxes, hence the box_centers parameter) on every rank, like the reference's replicated state
+    # (train_boxpose.py:407); a rank draws its own pixels (weak) or takes its slice of the one global batch (strong)
+    scene_rng = np.random.default_rng(S.SEED + 7)
+    c2w = S.random_c2w(scene_rng)
+    centers, ext_np = S.boxes_in_view(scene_rng, c2w, K)
+    rng = np.random.default_rng(S.SEED + 1007 + (0 if strong else rank))
+    rays_np, _ = S.random_rays(rng, B_all, c2w=c2w, far=40.0)
     rng_w = np.random.default_rng(S.SEED)                       # same weights on every rank
     mlp = S.glorot_mlp(rng_w, 60, 256, 0.0)
     box_mlps = [S.glorot_mlp(rng_w, 63, 128, 0.0) for _ in range(K)]
@@ -271,6 +275,7 @@ def train_bench(dev, rank, world, steps, warmup, precision, pose=False, global_b
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / k
         if world > 1:
+            print(f"[train_bench] rank {rank}: {ms:.3f} ms/step (local)", file=sys.stderr)
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t[0])

@@ -11,6 +11,7 @@ CUDA graph and replayed (`GraphedTrainStep`): at the reference's shipped batch o
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional
 
@@ -127,9 +128,18 @@ def train_step(model: MipNerfModel, config: Config, rng, state: TrainState, batc
         wl2 = (config.weight_decay_mult / n) * (v.flat * v.flat).sum().reshape(1)
         d_flat.add_(v.flat, alpha=2.0 * config.weight_decay_mult / n)
     stats, grads = loss_and_grads(model, config, ret, batch, eps_, tv=tv, weight_l2=wl2, workspace=workspace)
-    side = parallel.GradientBuckets(v, d_flat, world_size) if world_size > 1 else None
+    # jax.lax.pmean(grad, 'batch') (:253): per-network buckets all-reduced on a side stream while the backward continues
+    # (DURF_ALLREDUCE=single: one all-reduce of the whole flat gradient after the backward, the round-1 behaviour)
+    bucketed = world_size > 1 and os.environ.get('DURF_ALLREDUCE', 'buckets') == 'buckets'
+    side = parallel.GradientBuckets(v, d_flat, world_size) if bucketed else None
     model.backward(v, ctx, grads, d_flat, on_network_done=None if side is None else side.network_done)
-    scale = side.finish() if side is not None else 1.0                        # jax.lax.pmean(grad, 'batch'), :253
+    if side is not None:
+        scale = side.finish()
+    else:
+        if world_size > 1 and os.environ.get('DURF_ALLREDUCE') == 'none':     # diagnosis only: replicas drift apart
+            scale = 1.0 / world_size
+        else:
+            scale = parallel.allreduce_gradients(d_flat) if world_size > 1 else 1.0
     sumsq = torch.zeros(1, device=d_flat.device)
     ops.grad_sanitize(d_flat, config.grad_max_val, scale, sumsq)
     if dev_mode:
