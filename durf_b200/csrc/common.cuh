@@ -34,6 +34,9 @@ void count_launch(int n = 1);
   } while (0)
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+// true if every non-null pointer is 16-byte aligned (rows moved with 128-bit loads / stores)
+template <class... P>
+static inline bool aligned16(const P*... p) { return ((... | reinterpret_cast<uintptr_t>(p)) & 15u) == 0; }
 
 // ---- device helpers ---------------------------------------------------------------------------
 constexpr int kWarp = 32;

@@ -229,6 +229,9 @@ extern "C" int durf_composite_fwd(durf_stream_t stream, const DurfCompositeArgs*
   if (rc != DURF_OK) return rc;
   if (args->B == 0) return DURF_OK;
   DURF_REQUIRE(args->comp_rgb && args->depth && args->acc && args->weights, DURF_E_INVALID, "durf_composite_fwd: null output");
+  // N = 128 rows are moved with 16-byte loads / stores
+  DURF_REQUIRE(args->N != 128 || aligned16(args->raw_rgb, args->raw_density, args->weights, args->t_mids, args->t_dists), DURF_E_INVALID,
+               "durf_composite_fwd: raw_rgb / raw_density / weights / t_mids / t_dists must be 16-byte aligned when N = 128");
   composite_fwd_kernel<<<ceil_div(args->B, 4), 128, 0, (cudaStream_t)stream>>>(*args);
   DURF_CHECK_LAUNCH("durf_composite_fwd");
   return DURF_OK;
@@ -242,6 +245,8 @@ extern "C" int durf_composite_bwd(durf_stream_t stream, const DurfCompositeArgs*
   if (args->B == 0) return DURF_OK;
   DURF_REQUIRE(d_comp_rgb && d_depth && d_weights && d_raw_rgb && d_raw_density, DURF_E_INVALID,
                "durf_composite_bwd: null gradient buffer");
+  DURF_REQUIRE(args->N != 128 || aligned16(args->raw_rgb, args->raw_density, d_weights, d_raw_rgb, d_raw_density), DURF_E_INVALID,
+               "durf_composite_bwd: raw_rgb / raw_density / d_weights / d_raw_rgb / d_raw_density must be 16-byte aligned when N = 128");
   composite_bwd_kernel<<<ceil_div(args->B, 4), 128, 0, (cudaStream_t)stream>>>(*args, d_comp_rgb, d_depth, d_acc, d_weights,
                                                                                 d_raw_rgb, d_raw_density, d_dirs);
   DURF_CHECK_LAUNCH("durf_composite_bwd");

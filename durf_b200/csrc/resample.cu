@@ -185,7 +185,7 @@ extern "C" int durf_resample_fwd(durf_stream_t stream, int32_t B, int32_t N, con
   p.s_jit = (float)(s - eps32);
   p.u_max = (float)(1.0 - eps32);
   p.out = new_t_vals;
-  if (N == 128 && num_samples == 129) {
+  if (N == 128 && num_samples == 129 && aligned16(weights)) {       // the specialisation reads the weights with 16-byte loads
     resample128_kernel<<<ceil_div(B, 4), 128, 0, (cudaStream_t)stream>>>(p);
   } else {
     const size_t smem = 4 * (3 * (N + 1) + 1) * sizeof(float);

@@ -103,7 +103,8 @@ int durf_obb_frontend_bwd(durf_stream_t stream, int32_t B, int32_t K,
 
 /* Compaction of the rays that hit object k (the reference evaluates every BoxMLP on every ray and
  * multiplies by the 0/1 mask, obbpose_model.py:174-201; evaluating only hit rays is result-identical).
- * ray_index [B] receives the indices (ascending) and *count their number. */
+ * ray_index [B] receives the indices (in NO particular order: warp-aggregated atomics; every consumer scatters its
+ * results back per ray) and *count their number. */
 int durf_compact_hits(durf_stream_t stream, int32_t B, int32_t K, int32_t k, const int32_t* hit,
                       int32_t* ray_index, int32_t* count);
 
@@ -218,6 +219,8 @@ typedef struct DurfCompositeArgs {
   int32_t white_bkgd, rand_bkgd;
   int32_t activated;           /* 0: inputs are raw (sigmoid / softplus(x + density_bias) applied here); 1: inputs are rgb / density (mip.volumetric_rendering's own signature) */
   float density_bias;          /* -1 (obbpose_model.py:58) */
+  /* N = 128: raw_rgb, raw_density, weights, t_mids, t_dists (and the gradient buffers of durf_composite_bwd) are moved with
+   * 16-byte loads / stores and must be 16-byte aligned (DURF_E_INVALID otherwise); t_vals rows are 516 bytes, 4-byte aligned. */
   const float* raw_rgb;        /* [B,N,3] summed raw colour (obbpose_model.py:233) */
   const float* raw_density;    /* [B,N]   summed raw density (+ optional noise already added) */
   const float* t_vals;         /* [B,N+1] */

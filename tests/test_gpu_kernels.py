@@ -303,6 +303,11 @@ def test_mlp_tensor_core_forward(topo, M):
     rel = lambda a, b: float((a - b).norm() / b.norm())
     assert rel(rgb, want_rgb) <= 2e-2, f"raw_rgb rel Frobenius {rel(rgb, want_rgb):.3e}"
     assert rel(den, want_den[..., 0]) <= 2e-2, f"raw_density rel Frobenius {rel(den, want_den[..., 0]):.3e}"
+    # against the oracle with the kernel's bf16 rounding points made explicit (operands bf16, accumulation / biases / heads
+    # fp32): what is left is the summation order of the fp32 accumulation and rare 1-ulp bf16 rounding flips -> 2e-3
+    emu_rgb, emu_den = H.mlp_apply_bf16_emulated([(torch.from_numpy(k), torch.from_numpy(b)) for k, b in layers], ot, x, cond)
+    assert rel(rgb, emu_rgb) <= 2e-3, f"raw_rgb vs bf16-emulated oracle: rel Frobenius {rel(rgb, emu_rgb):.3e}"
+    assert rel(den, emu_den[..., 0]) <= 2e-3, f"raw_density vs bf16-emulated oracle: rel Frobenius {rel(den, emu_den[..., 0]):.3e}"
 
 
 def test_mlp_tensor_core_forward_edge_counts():

@@ -217,8 +217,9 @@ def test_train_step_tensor_core():
 
 
 def test_pose_optimisation_with_tensor_core_background():
-    """C5 with precision='bf16': the background MLP trains on the tensor cores, the object MLPs fall to the fp32 kernels
-    (they own the input gradient that reaches the SE(3) box parameters).  d box_centers vs fp64 oracle: cosine >= 0.98."""
+    """C5 with precision='bf16': the background MLP and the width-128 object MLPs all train on the tensor cores; the dgrad
+    chain's extra stage delivers the input gradient that reaches the SE(3) box parameters through durf_raymarch_bwd and
+    durf_obb_frontend_bwd.  d box_centers vs the fp64 oracle: cosine >= 0.98."""
     from durf_b200.train import TrainState, train_step
     from durf_b200.utils import Config
     sc = H.scene(B=256, K=2, seed=31)
