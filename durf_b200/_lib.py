@@ -122,6 +122,9 @@ SIGNATURES = {
     "durf_mlp_saved_bytes": (C.c_size_t, [C.POINTER(MlpTopology), _i32, _i32, _i32]),
     "durf_mlp_fwd": (C.c_int, [_vp, C.POINTER(MlpArgs)]),
     "durf_mlp_bwd": (C.c_int, [_vp, C.POINTER(MlpArgs), _vp, _vp, _vp, _vp]),
+    "durf_mlp_bwd_flags_bytes": (C.c_size_t, [C.POINTER(MlpTopology), _i32]),
+    "durf_mlp_bwd_data": (C.c_int, [_vp, C.POINTER(MlpArgs), _vp, _vp, _vp, _vp, _i32]),
+    "durf_mlp_bwd_weights": (C.c_int, [_vp, C.POINTER(MlpArgs), _vp, _vp, _vp, _vp, _i32]),
     "durf_composite_fwd": (C.c_int, [_vp, C.POINTER(CompositeArgs)]),
     "durf_composite_bwd": (C.c_int, [_vp, C.POINTER(CompositeArgs), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "durf_resample_fwd": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _f, _i32, _i32, _vp]),

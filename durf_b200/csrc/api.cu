@@ -35,6 +35,10 @@ int64_t mlp_tc_packed_t_bytes(const DurfMlpTopology& t);
 int mlp_tc_pack_t(cudaStream_t st, const DurfMlpTopology& t, const float* params, void* packed_t);
 int mlp_tc_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density, float* d_params,
                     float* d_features);
+int mlp_tc_backward_data(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density,
+                         float* d_features, int32_t* tile_done, int max_ctas);
+int mlp_tc_backward_weights(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density,
+                            float* d_params, const int32_t* tile_done, int max_ctas);
 
 }  // namespace durf
 
@@ -121,4 +125,29 @@ extern "C" int durf_mlp_bwd(durf_stream_t stream, const DurfMlpArgs* args, const
   if (args->precision == DURF_PREC_FP32)
     return mlp_fp32_backward((cudaStream_t)stream, *args, d_raw_rgb, d_raw_density, d_params, d_features);
   return mlp_tc_backward((cudaStream_t)stream, *args, d_raw_rgb, d_raw_density, d_params, d_features);
+}
+
+extern "C" size_t durf_mlp_bwd_flags_bytes(const DurfMlpTopology* topo, int32_t M) {
+  if (!topology_ok(topo) || M < 0) return 0;
+  return (size_t)M * (topo->depth + 2) * sizeof(int32_t);
+}
+
+extern "C" int durf_mlp_bwd_data(durf_stream_t stream, const DurfMlpArgs* args, const float* d_raw_rgb, const float* d_raw_density,
+                                 float* d_features, int32_t* tile_done, int32_t max_ctas) {
+  int rc = check_mlp(args, "durf_mlp_bwd_data");
+  if (rc != DURF_OK) return rc;
+  DURF_REQUIRE(args->precision == DURF_PREC_BF16, DURF_E_UNSUPPORTED, "durf_mlp_bwd_data: tensor-core (BF16) path only");
+  DURF_REQUIRE(d_raw_rgb && d_raw_density, DURF_E_INVALID, "durf_mlp_bwd_data: null gradient buffer");
+  if (args->M == 0) return DURF_OK;
+  return mlp_tc_backward_data((cudaStream_t)stream, *args, d_raw_rgb, d_raw_density, d_features, tile_done, max_ctas);
+}
+
+extern "C" int durf_mlp_bwd_weights(durf_stream_t stream, const DurfMlpArgs* args, const float* d_raw_rgb, const float* d_raw_density,
+                                    float* d_params, const int32_t* tile_done, int32_t max_ctas) {
+  int rc = check_mlp(args, "durf_mlp_bwd_weights");
+  if (rc != DURF_OK) return rc;
+  DURF_REQUIRE(args->precision == DURF_PREC_BF16, DURF_E_UNSUPPORTED, "durf_mlp_bwd_weights: tensor-core (BF16) path only");
+  DURF_REQUIRE(d_raw_rgb && d_raw_density && d_params, DURF_E_INVALID, "durf_mlp_bwd_weights: null gradient buffer");
+  if (args->M == 0) return DURF_OK;
+  return mlp_tc_backward_weights((cudaStream_t)stream, *args, d_raw_rgb, d_raw_density, d_params, tile_done, max_ctas);
 }

@@ -497,6 +497,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     uint32_t stg_buf = 0;                         // SAVE: which of this warp's two 4 KB staging pieces the next epilogue fills
     const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 128;
     long long e_acc = 0, e_ld = 0, e_math = 0, e_st = 0, e_begin = clock64(), eq = 0, e_m0 = 0, e_ld1 = 0, e_m1 = 0;
+    const bool trs = DURF_TRACE_DETAIL && tr;
+    long long sv_wg = 0, sv_fill = 0, sv_fence = 0, sv_issue = 0, sq = 0;
     // Per-tile housekeeping (raw outputs of the PREVIOUS tile, view bias of this one) is deferred until after layer 0's
     // epilogues, when the tensor core has a whole layer of MMAs queued: the tile boundary costs the issuer nothing.
     float den_prev = 0.f, rgb_prev[3] = {0.f, 0.f, 0.f};
@@ -551,8 +553,10 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
           };
           // training: one warp's 32 rows x 64 columns of a saved activation (and their 1-bit ReLU mask words)
           auto save_piece = [&](const uint32_t (&pk)[NG][16], bool with_mask) {
+            if (trs) sq = clock64();
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the piece filled two epilogues ago was read
             __syncwarp();
+            if (trs) { sv_wg += clock64() - sq; sq = clock64(); }
             const uint32_t sdst = sbase + C::OFF_STG + ((stg_buf * 8 + (warp - 4)) << 12) + (lane >> 3) * 1024 + (lane & 7) * 128;
 #pragma unroll
             for (int i = 0; i < NG; ++i) {
@@ -572,14 +576,21 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
                              "r"(pk[i][4 * q4]), "r"(pk[i][4 * q4 + 1]), "r"(pk[i][4 * q4 + 2]), "r"(pk[i][4 * q4 + 3]) : "memory");
             }
             __syncwarp();
+            if (trs) { sv_fill += clock64() - sq; sq = clock64(); }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (trs) { sv_fence += clock64() - sq; sq = clock64(); }
             if (lane == 0) {
-              uint8_t* gdst = p.saved + ((size_t)tile * p.saved_blocks_per_tile + g * C::KB + (col0 >> 6)) * kBlockBytes + q * 4096;
+              // record of layer g: [sample half][64-column block][64 rows x 128 B], so that the weight-gradient kernel fetches the
+              // 64 samples of ALL the layer's blocks with one contiguous bulk copy; this warp's 32 rows are 4 KB of it
+              const int nb = 2 * n_halves;            // 64-column blocks of this layer's output
+              uint8_t* gdst = p.saved + ((size_t)tile * p.saved_blocks_per_tile + g * C::KB) * kBlockBytes +
+                              (size_t)(q >> 1) * nb * 8192 + (col0 >> 6) * 8192 + (q & 1) * 4096;
               if (valid)
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(gdst),
                              "r"(sbase + C::OFF_STG + ((stg_buf * 8 + (warp - 4)) << 12)) : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+            if (trs) sv_issue += clock64() - sq;
             stg_buf ^= 1;
           };
           uint32_t v[NG][32];
@@ -684,6 +695,8 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       if (tr && !more(tile + (int)gridDim.x))
         printf("durf mlp_tc trace: epilogue thread: total %lld cyc; waiting acc_full %lld, tmem ld %lld, math+st issue %lld (g0 %lld, ld1 wait %lld, g1 %lld), st wait %lld\n",
                clock64() - e_begin, e_acc, e_ld, e_math, e_m0, e_ld1, e_m1, e_st);
+      if (SAVE && trs && !more(tile + (int)gridDim.x))
+        printf("durf mlp_tc trace: save_piece: wait_group %lld, masks + st.shared %lld, fence.proxy.async %lld, bulk-store issue %lld\n", sv_wg, sv_fill, sv_fence, sv_issue);
       // stash this tile's head results: they are combined and written while the next tile's layer 1 runs
       if (ch == 1) {
         s_part[row] = den; s_part[128 + row] = rgb[0]; s_part[256 + row] = rgb[1]; s_part[384 + row] = rgb[2];

@@ -12,12 +12,15 @@
 //   dX = dZ_0 W_0^T + dZ_skip W_skip[width:]^T   (64 columns, fp32 rows)
 // that the box-pose path needs; dZ_skip waits in a third TMEM buffer.  The background branch needs no input gradient
 // (its samples depend on no parameter).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 #include "mlp_topology.h"
 
 namespace durf {
 
 constexpr int kDgMaxStages = 12;
+constexpr int kMailSlots = 32;        // per epilogue warp: dZ pieces whose completion is known but not yet published
 
 struct DgStage {
   int n_halves;     // output columns / 128 (1 for the 64-column input-gradient stage)
@@ -53,6 +56,12 @@ struct DgParams {
   float* d_features;         // [opt] [M*128, in_dim] fp32 gradient w.r.t. the input features (object MLPs, box-pose path)
   int in_dim;
   int trace;
+  // [opt] overlap with the weight-gradient kernel running on other SMs: tile_done[tile * flag_stride + layer slot] counts the
+  // pieces of that layer's dZ that are complete in global memory (one release-increment per epilogue warp and N-half); the
+  // consumer acquires it before it fetches the blocks (mlp_tc_wgrad.cu)
+  int32_t* flags;
+  int flag_stride;
+  int max_ctas;              // 0: one CTA per SM
   DgStage st[kDgMaxStages];
 };
 
@@ -72,7 +81,8 @@ struct DgCfg {
   static constexpr int OFF_WDEN = OFF_OUT + 8 * 4096;                 // fp32 [W]
   static constexpr int OFF_WRGB = OFF_WDEN + W * 4;                   // fp32 [128][4] (rgb head kernel rows, padded)
   static constexpr int OFF_MISC = OFF_WRGB + 128 * 4 * 4;
-  static constexpr int MISC_BYTES = 512;
+  static constexpr int MISC_BYTES = 2048;                             // tmem ptr + barriers (256 B) | publisher mailboxes
+  static constexpr int OFF_MAIL = OFF_MISC + 256;                     // [8] heads (128 B) | [8][kMailSlots] counter offsets
   static constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -138,7 +148,7 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
   auto bar_acc_full = [&](int h) { return bar0 + 8 * (16 + h); };
   auto bar_a_ready = [&](int h) { return bar0 + 8 * (18 + h); };
   const uint32_t bar_p_ready = bar0 + 8 * 20;
-  static_assert(16 + 8 * 21 <= C::MISC_BYTES, "barrier area");
+  static_assert(16 + 8 * 21 <= 256 && 256 + 128 + 8 * kMailSlots * 4 <= C::MISC_BYTES, "barrier area + mailboxes");
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
@@ -146,6 +156,7 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
     mbar_init(bar_p_ready, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x < 32) reinterpret_cast<uint32_t*>(smem + C::OFF_MAIL)[threadIdx.x] = 0;      // mailbox heads
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(C::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -186,6 +197,8 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
       uint32_t stage = 0, phase = 0, ar_par[2] = {0, 0}, pr_par = 0;
       int it = 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const bool tr = DURF_TRACE_DETAIL && p.trace && blockIdx.x == 0;
+      long long t_begin = clock64(), t_start = 0, tq = 0;
       // Barrier waits are software-pipelined as in the forward kernel (umma_kblock_conv): each K block of MMAs probes the
       // barriers of the NEXT K block before its MMAs and consumes the outcome after them, because a wait executed between
       // two groups of MMAs returns only once the tensor queue has drained.
@@ -200,9 +213,11 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
           for (int nh = 0; nh < S.n_halves; ++nh) {
             const uint32_t d_addr = tmem_u + C::ACC_COL + nh * 128;
             if (s == 0 && nh == 0) {
+              if (tr) tq = clock64();
               if (it > 0)      // accumulators of the previous tile's last stage must have been drained
                 for (int h = 0; h < last_halves; ++h) { mbar_wait(bar_a_ready(h), ar_par[h]); ar_par[h] ^= 1; }
               mbar_wait(bar_p_ready, pr_par); pr_par ^= 1;           // dZ_cond is in TMEM
+              if (tr) t_start += clock64() - tq;
             }
             tc_fence_after();      // this chunk's weights (and its first K block) were waited for by the previous K block
             // the chunk after this one: (s, nh+1), else (s+1, 0), else the next tile's first
@@ -236,6 +251,38 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
           }
         }
       }
+      if (tr && lane == 0) printf("durf dgrad trace: MMA thread: %d tiles, total %lld cyc; tile start (drained accumulators, dZ_cond) %lld\n",
+                                  it, clock64() - t_begin, t_start);
+    }
+  } else if (warp == 3) {
+    // ===== publisher: lane l < 8 drains the mailbox of epilogue warp l.  One gpu-scope fence per batch (it orders the dZ
+    // pieces, whose completion the epilogue warps observed before they posted, before the increments), then one relaxed
+    // increment per piece: fence + relaxed atomic = release.  The fence's latency is hidden in this warp. =====
+    if (p.flags) {
+      const uint32_t head_addr = smem_u32(smem + C::OFF_MAIL) + (lane & 7) * 16;
+      const int* ring = reinterpret_cast<const int*>(smem + C::OFF_MAIL + 128) + (lane & 7) * kMailSlots;
+      uint32_t tail = 0;
+      long long t0 = 0;
+      while (true) {
+        uint32_t h = 0x80000000u;                   // lanes >= 8: nothing to do, done
+        if (lane < 8) asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(h) : "r"(head_addr) : "memory");
+        const bool fin = (h >> 31) != 0;
+        h &= 0x7FFFFFFFu;
+        if (lane >= 8) h = tail;
+        const bool fresh = h != tail;
+        if (__any_sync(kFull, fresh)) {
+          __threadfence();
+          for (; tail != h; ++tail)
+            asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(p.flags + ring[tail & (kMailSlots - 1)]) : "memory");
+          t0 = 0;
+        } else {
+          __nanosleep(200);
+          const long long now = clock64();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 8000000000LL) { printf("durf dgrad kernel: publisher of block %d timed out\n", blockIdx.x); __trap(); }
+        }
+        if (__all_sync(kFull, fin && tail == h)) break;
+      }
     }
   } else if (warp >= 4) {
     // ===== epilogue: thread = sample row; warps q and q+4 share TMEM lane quarter q and split a half's 128 columns =====
@@ -244,7 +291,28 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t af_par[2] = {0, 0};
     uint32_t mw_next[2] = {0, 0};                 // mask words of the next masked epilogue, fetched one epilogue ahead
+    // counters (offsets into p.flags, -1 = none) of this warp's kPubDepth most recent dZ pieces, oldest first: a piece is
+    // published once at most kPubDepth - 1 younger bulk stores are still pending (cp.async.bulk.wait_group), i.e. kPubDepth
+    // epilogues (~15 k cycles) after it was staged - a store's completion in L2 takes several microseconds under load, and a
+    // shorter queue stalled the epilogue (the critical path of this kernel) on it
+    constexpr int kPubDepth = 6;
+    // The release itself (a gpu-scope fence: ~1.5 k cycles, it waits for the SM's outstanding stores) is NOT executed here:
+    // lane 0 drops the counter's offset into this warp's mailbox and the otherwise idle warp 3 publishes it.
+    uint32_t* mail_head = reinterpret_cast<uint32_t*>(smem + C::OFF_MAIL) + (warp - 4) * 4;
+    int* mail_ring = reinterpret_cast<int*>(smem + C::OFF_MAIL + 128) + (warp - 4) * kMailSlots;
+    uint32_t mail_n = 0;
+    auto mail_push = [&](int off) {
+      mail_ring[mail_n & (kMailSlots - 1)] = off;
+      ++mail_n;
+      asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(mail_head)), "r"(mail_n) : "memory");
+    };
+    int pq[kPubDepth];
+#pragma unroll
+    for (int i = 0; i < kPubDepth; ++i) pq[i] = -1;
+    const bool tr = DURF_TRACE_DETAIL && p.trace && blockIdx.x == 0 && threadIdx.x == 128;
+    long long e_begin = clock64(), e_pro = 0, e_acc = 0, e_wg = 0, e_work = 0, e_pub = 0, eq = 0, e_fence = 0, e_issue = 0, e_mask = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (tr) eq = clock64();
       const int ray = p.ray_index ? p.ray_index[tile] : tile;
       const uint8_t* sv = p.saved + (size_t)tile * p.saved_blocks * kBlockBytes;
       uint8_t* dzt = p.dz + (size_t)tile * p.saved_blocks * kBlockBytes;
@@ -253,14 +321,18 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
         const float* g3 = p.d_raw_rgb + ((size_t)ray * kTileM + row) * 3;
         const float g0 = g3[0], g1 = g3[1], g2 = g3[2];
         const int c0 = ch * 64;                                   // columns [c0, c0 + 64) = block ch of the condition slot
-        const uint8_t* act = sv + (size_t)(p.cond_slot + ch) * kBlockBytes;
-        uint8_t* out = dzt + (size_t)(p.cond_slot + ch) * kBlockBytes;
+        // layer records are [sample half][64-column block][64 rows x 128 B] (see mlp_tc.cu, save_piece); the condition layer has
+        // two blocks
+        const size_t cond_off = (size_t)p.cond_slot * kBlockBytes + (size_t)(row >> 6) * (2 * 8192) + ch * 8192;
+        const uint8_t* act = sv + cond_off;
+        uint8_t* out = dzt + cond_off;
+        const uint32_t row64 = row & 63;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           uint32_t pk[16];
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
-            const uint4 a4 = *reinterpret_cast<const uint4*>(act + sw128_offset(row, i * 4 + c8));
+            const uint4 a4 = *reinterpret_cast<const uint4*>(act + sw128_offset(row64, i * 4 + c8));
             const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -269,7 +341,7 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
               const float v0 = fmaf(g2, w0.z, fmaf(g1, w0.y, g0 * w0.x)), v1 = fmaf(g2, w1.z, fmaf(g1, w1.y, g0 * w1.x));
               pk[c8 * 4 + e] = mask_pair(cvt_bf16x2(v0, v1), aw[e]);
             }
-            *reinterpret_cast<uint4*>(out + sw128_offset(row, i * 4 + c8)) =
+            *reinterpret_cast<uint4*>(out + sw128_offset(row64, i * 4 + c8)) =
                 make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
           }
           tmem_st16(t_lane + C::ACT_COL + (c0 + i * 32) / 2, pk);     // A operand of stage 0 = activation buffer 0
@@ -277,7 +349,13 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_p_ready);
+        if (p.flags) {             // dZ_cond went out with generic stores: fence each thread's, then one increment per warp
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) mail_push(tile * p.flag_stride + p.cond_slot / C::KB);
+        }
       }
+      if (tr) e_pro += clock64() - eq;
       const float gden = p.d_raw_density[(size_t)ray * kTileM + row];
       const uint32_t my_out = sbase + C::OFF_OUT + ((warp - 4) << 12);
       const uint32_t row_off = (lane >> 3) * 1024 + (lane & 7) * 128, r7 = lane & 7;
@@ -298,7 +376,9 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
         const bool feeds_next = S.o_sel >= 0;
         for (int h = 0; h < S.n_halves; ++h) {
           const int col0 = h * 128 + ch * 64;
+          if (tr) eq = clock64();
           mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
+          if (tr) { e_acc += clock64() - eq; eq = clock64(); }
           tc_fence_after();
           if (S.kind == 3) {
             // input gradient: 64 accumulator columns (the in_dim features), fp32 rows straight to d_features
@@ -316,9 +396,20 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
           }
           uint32_t v[32];
           tmem_ld32_issue(t_lane + C::ACC_COL + col0, v);
-          const uint32_t mw[2] = {mw_next[0], mw_next[1]};
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // previous dZ piece was read out
+          uint32_t mw[2] = {mw_next[0], mw_next[1]};
+          if (tr) { asm volatile("" : "+r"(mw[0]), "+r"(mw[1])); e_mask += clock64() - eq; eq = clock64(); }
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // previous dZ piece was read out
+            if (p.flags) {
+              asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPubDepth - 1) : "memory");     // the oldest queued piece is in HBM / L2
+              if (pq[0] >= 0) mail_push(pq[0]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i + 1 < kPubDepth; ++i) pq[i] = pq[i + 1];
+          pq[kPubDepth - 1] = p.flags ? tile * p.flag_stride + S.out_slot / C::KB : -1;
           __syncwarp();
+          if (tr) { e_wg += clock64() - eq; eq = clock64(); }
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             tmem_ld_wait();
@@ -335,21 +426,33 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
           if (feeds_next || S.to_skip) tmem_st_wait();
           tc_fence_before();
           mbar_arrive(bar_a_ready(h));     // next stage's A operand half is in TMEM (last stage: accumulators drained)
+          if (tr) { e_work += clock64() - eq; eq = clock64(); }
           // off the critical path: publish the dZ piece, fetch the next epilogue's mask piece
           __syncwarp();
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (tr) { e_fence += clock64() - eq; eq = clock64(); }
           if (lane == 0) {
-            uint8_t* gdst = dzt + (size_t)(S.out_slot + (col0 >> 6)) * kBlockBytes + q * 4096;
+            uint8_t* gdst = dzt + (size_t)S.out_slot * kBlockBytes + (size_t)(q >> 1) * (C::KB * 8192) + (col0 >> 6) * 8192 + (q & 1) * 4096;
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(gdst), "r"(my_out) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (tr) { e_issue += clock64() - eq; eq = clock64(); }
           int h2 = h + 1, s2 = s;
           if (h2 >= S.n_halves) { h2 = 0; ++s2; while (s2 < p.n_stages && !p.st[s2].last_part) ++s2; }    // next entry with an epilogue
           if (s2 < p.n_stages && (p.st[s2].kind == 1 || p.st[s2].kind == 2)) fetch_mask(s2, h2);
+          if (tr) e_pub += clock64() - eq;
         }
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every staged dZ piece is in HBM
+    if (tr) printf("durf dgrad trace: epilogue thread: total %lld cyc; prologue %lld, waiting acc_full %lld, mask words arrive %lld, bulk wait_group %lld, ld+pack+st+arrive %lld, fence %lld, bulk-store issue %lld, next-stage lookup + mask fetch %lld\n",
+                   clock64() - e_begin, e_pro, e_acc, e_mask, e_wg, e_work, e_fence, e_issue, e_pub);
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every staged dZ piece is in HBM
+#pragma unroll
+      for (int i = 0; i < kPubDepth; ++i)
+        if (pq[i] >= 0) mail_push(pq[i]);
+      if (p.flags) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(mail_head)), "r"(mail_n | 0x80000000u) : "memory");   // done
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -475,11 +578,25 @@ int mlp_tc_dgrad_launch(cudaStream_t st, const DurfMlpTopology& t, const DgParam
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = P.M < sms ? P.M : sms;
+  if (P.max_ctas > 0 && P.max_ctas < sms) sms = P.max_ctas;
+  int grid = P.M < sms ? P.M : sms;
   cudaError_t e;
   if (t.width == 256) {
     e = cudaFuncSetAttribute(mlp_tc_dgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DgCfg<256>::SMEM_BYTES);
     DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_bwd(bf16): smem attribute: %s", cudaGetErrorString(e));
+    if (P.flags && grid >= 2) {
+      // sharing the GPU with the weight-gradient kernel: launched as CTA pairs so that the two SMs of a TPC run the SAME kernel
+      // (the CTAs do not communicate)
+      grid &= ~1;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = DgCfg<256>::SMEM_BYTES; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, mlp_tc_dgrad_kernel<256>, P);
+      DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_bwd(bf16): dgrad launch: %s", cudaGetErrorString(e));
+    } else
     mlp_tc_dgrad_kernel<256><<<grid, 384, DgCfg<256>::SMEM_BYTES, st>>>(P);
   } else {
     e = cudaFuncSetAttribute(mlp_tc_dgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DgCfg<128>::SMEM_BYTES);
@@ -499,30 +616,53 @@ struct WgradParams;
 int64_t mlp_tc_packed_bytes(const DurfMlpTopology& t);
 int mlp_tc_wgrad_run(cudaStream_t st, const DurfMlpTopology& t, const uint8_t* saved, const uint8_t* feat, const uint8_t* dz,
                      const float* d_raw_rgb, const float* d_raw_density, const float* cond, const int32_t* ray_index,
-                     const int32_t* count, int M, float* d_params);
+                     const int32_t* count, int M, float* d_params, const int32_t* tile_done, int max_ctas);
 
-int mlp_tc_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density, float* d_params,
-                    float* d_features) {
+// The two halves of the tensor-core backward.  `tile_done` (may be NULL) is the [M, depth + 2] counter array through which
+// the data-gradient kernel tells a concurrently running weight-gradient kernel which dZ blocks are complete.
+static int tc_bwd_check(const DurfMlpArgs& a, const char* who) {
+  const DurfMlpTopology& t = a.topo;
+  DURF_REQUIRE(mlp_tc_bwd_supported(t), DURF_E_UNSUPPORTED, "%s: no tensor-core backward for this topology", who);
+  DURF_REQUIRE(a.N == kTileM, DURF_E_UNSUPPORTED, "%s: needs 128 samples per ray (got %d)", who, a.N);
+  DURF_REQUIRE(a.saved && a.packed && a.features, DURF_E_INVALID, "%s: needs saved activations, weight images, feature tiles", who);
+  const size_t need = (size_t)a.M * mlp_tc_saved_blocks(t) * kBlockBytes;
+  DURF_REQUIRE(a.workspace && a.workspace_bytes >= need, DURF_E_WORKSPACE, "%s: workspace %zu < %zu bytes", who, a.workspace_bytes, need);
+  return DURF_OK;
+}
+
+int mlp_tc_backward_data(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density,
+                         float* d_features, int32_t* tile_done, int max_ctas) {
   DURF_REQUIRE(d_features == nullptr || a.topo.width == 128, DURF_E_UNSUPPORTED,
                "durf_mlp_bwd(bf16): the input gradient is available for width-128 networks (BoxMLP) only");
+  int rc = tc_bwd_check(a, "durf_mlp_bwd(bf16)");
+  if (rc != DURF_OK) return rc;
   const DurfMlpTopology& t = a.topo;
-  DURF_REQUIRE(mlp_tc_bwd_supported(t), DURF_E_UNSUPPORTED, "durf_mlp_bwd(bf16): no tensor-core backward for this topology");
-  DURF_REQUIRE(a.N == kTileM, DURF_E_UNSUPPORTED, "durf_mlp_bwd(bf16): needs 128 samples per ray (got %d)", a.N);
-  DURF_REQUIRE(a.saved && a.packed && a.features, DURF_E_INVALID, "durf_mlp_bwd(bf16): needs saved activations, weight images, feature tiles");
-  const size_t need = (size_t)a.M * mlp_tc_saved_blocks(t) * kBlockBytes;
-  DURF_REQUIRE(a.workspace && a.workspace_bytes >= need, DURF_E_WORKSPACE, "durf_mlp_bwd(bf16): workspace %zu < %zu bytes",
-               a.workspace_bytes, need);
   DgParams P{};
   P.saved = (const uint8_t*)a.saved; P.dz = (uint8_t*)a.workspace;
   P.masks = reinterpret_cast<const uint32_t*>(P.saved + (size_t)a.M * mlp_tc_saved_blocks(t) * kBlockBytes);
   P.depth = t.depth;
   P.packed_t = (const uint8_t*)a.packed + mlp_tc_packed_bytes(t);
   P.params = a.params; P.d_raw_rgb = d_raw_rgb; P.d_raw_density = d_raw_density;
-  P.ray_index = a.ray_index; P.count = a.count; P.M = a.M; P.trace = 0; P.d_features = d_features;
-  int rc = mlp_tc_dgrad_launch(st, t, P);
+  P.ray_index = a.ray_index; P.count = a.count; P.M = a.M; P.d_features = d_features;
+  P.flags = tile_done; P.flag_stride = t.depth + 2; P.max_ctas = max_ctas;
+  static const int trace_env = getenv("DURF_TC_TRACE") ? atoi(getenv("DURF_TC_TRACE")) : 0;
+  P.trace = trace_env;
+  return mlp_tc_dgrad_launch(st, t, P);
+}
+
+int mlp_tc_backward_weights(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density,
+                            float* d_params, const int32_t* tile_done, int max_ctas) {
+  int rc = tc_bwd_check(a, "durf_mlp_bwd(bf16)");
   if (rc != DURF_OK) return rc;
-  return mlp_tc_wgrad_run(st, t, (const uint8_t*)a.saved, (const uint8_t*)a.features, (const uint8_t*)a.workspace, d_raw_rgb,
-                          d_raw_density, a.cond, a.ray_index, a.count, a.M, d_params);
+  return mlp_tc_wgrad_run(st, a.topo, (const uint8_t*)a.saved, (const uint8_t*)a.features, (const uint8_t*)a.workspace, d_raw_rgb,
+                          d_raw_density, a.cond, a.ray_index, a.count, a.M, d_params, tile_done, max_ctas);
+}
+
+int mlp_tc_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density, float* d_params,
+                    float* d_features) {
+  int rc = mlp_tc_backward_data(st, a, d_raw_rgb, d_raw_density, d_features, nullptr, 0);
+  if (rc != DURF_OK) return rc;
+  return mlp_tc_backward_weights(st, a, d_raw_rgb, d_raw_density, d_params, nullptr, 0);
 }
 
 }  // namespace durf

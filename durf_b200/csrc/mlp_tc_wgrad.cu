@@ -40,6 +40,8 @@ struct WgradJob {
   int extra;        // 0 none; 1: density head (vec = d_raw_density); 2: rgb head (vec = d_raw_rgb); 3: view part of the condition layer
   int ex_off;       // float offset of the extra's kernel gradient
   int ex_b_off;     // float offset of the extra's bias gradient (-1: none)
+  int flag_idx;     // slot of this job's dZ inside a tile's row of completion counters (-1: the job reads no dZ)
+  int flag_need;    // counter value at which the dZ blocks of a tile are complete
 };
 
 struct WgradParams {
@@ -60,6 +62,11 @@ struct WgradParams {
   uint8_t cta_part[kMaxCtas];  // which share of the job's tiles
   uint8_t job_parts[kMaxJobs]; // CTAs bound to the job
   long long* trace;            // [opt] debugging (DURF_WGRAD_TRACE=1): cycles of every CTA
+  int trace_detail;            // DURF_WGRAD_TRACE=2: job 1's first CTA prints where its producer / MMA / aux threads waited
+  // [opt] running CONCURRENTLY with the data-gradient kernel (on other SMs): flags[tile * flag_stride + job.flag_idx] reaches
+  // job.flag_need when the tile's dZ blocks of that layer are complete in global memory (mlp_tc_dgrad.cu, publish_piece)
+  const int32_t* flags;
+  int flag_stride;
 };
 
 __device__ __forceinline__ void red_add(float* addr, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory"); }
@@ -95,69 +102,108 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
   const uint32_t tmem_base = *s_tmem;
 
   const int num_tiles = p.count ? min(*p.count, p.M) : p.M;
+  // The CTAs of a job take the tiles round-robin (tile = part, part + parts, ...): together they walk the tiles in index
+  // order, which is the order the data-gradient kernel produces them in when the two kernels overlap.
   const int my_job = p.cta_job[blockIdx.x], parts = p.job_parts[my_job];
-  const int per = (num_tiles + parts - 1) / parts;
-  const int t_begin = min(num_tiles, (int)p.cta_part[blockIdx.x] * per), t_end = min(num_tiles, t_begin + per);
-  const int my_tiles = t_end - t_begin;
+  const int t_begin = (int)p.cta_part[blockIdx.x], t_end = num_tiles, t_step = parts;
+  const int my_tiles = t_begin < num_tiles ? (num_tiles - t_begin + parts - 1) / parts : 0;
   const long long trace_t0 = clock64();
 
   if (warp == 0) {
     // ===== producer: per (job, tile, sample half) one stage: a_blocks + z_blocks half blocks of 8 KB =====
     if (lane == 0 && my_tiles > 0) {
       uint32_t stage = 0, phase = 0;
+      const bool trp = DURF_TRACE_DETAIL && p.trace_detail && my_job == 1 && p.cta_part[blockIdx.x] == 0;
+      long long w_flag = 0, w_empty = 0, tq = 0, t_all = clock64();
       for (int j = my_job; j == my_job; ++j) {
         const WgradJob jb = p.jobs[j];
         const uint8_t* a_base = jb.a_src ? p.feat : p.saved;
         const size_t a_stride = (size_t)(jb.a_src ? 1 : p.saved_blocks) * kBlockBytes;
-        for (int tile = t_begin; tile < t_end; ++tile)
+        for (int tile = t_begin; tile < t_end; tile += t_step)
           for (int half = 0; half < 2; ++half) {
+            if (trp) tq = clock64();
+            if (half == 0 && p.flags && jb.flag_idx >= 0) {
+              // overlap with dgrad: wait until this tile's dZ blocks are complete (acquire), then order the generic-proxy
+              // acquire before the async-proxy reads of the bulk copies below.  A protocol bug traps instead of hanging.
+              const int32_t* f = p.flags + (size_t)tile * p.flag_stride + jb.flag_idx;
+              int v;
+              long long t0 = 0;
+              while (true) {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (v >= jb.flag_need) break;
+                __nanosleep(200);
+                const long long now = clock64();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000LL) {
+                  printf("durf wgrad kernel: tile %d of job %d never completed (counter %d of %d)\n", tile, my_job, v, jb.flag_need);
+                  __trap();
+                }
+              }
+              asm volatile("fence.proxy.async.global;" ::: "memory");
+            }
+            if (trp) { w_flag += clock64() - tq; tq = clock64(); }
             mbar_wait(bar_empty(stage), phase ^ 1);
+            if (trp) w_empty += clock64() - tq;
             mbar_arrive_expect_tx(bar_full(stage), (jb.a_blocks + jb.z_blocks) * kHalfBlock);
             const uint32_t dst = sbase + stage * kWgStageBytes;
-            for (int b = 0; b < jb.a_blocks; ++b)
-              bulk_g2s(dst + b * kHalfBlock, a_base + (size_t)tile * a_stride + (size_t)(jb.a_off + b) * kBlockBytes + half * kHalfBlock,
-                       kHalfBlock, bar_full(stage));
-            for (int b = 0; b < jb.z_blocks; ++b)
-              bulk_g2s(dst + (4 + b) * kHalfBlock,
-                       p.dz + ((size_t)tile * p.dz_blocks + jb.z_off + b) * kBlockBytes + half * kHalfBlock, kHalfBlock, bar_full(stage));
+            // layer records are [sample half][64-column block][64 rows x 128 B]: the 64 samples of all blocks of a layer are ONE
+            // contiguous piece of up to 32 KB (8 KB pieces stream at a third of the per-SM rate of 32 KB ones:
+            // profiles/r01_ubench_stream.log); an input-feature tile is a single 128-row block image
+            if (jb.a_src)
+              bulk_g2s(dst, a_base + (size_t)tile * a_stride + half * kHalfBlock, kHalfBlock, bar_full(stage));
+            else
+              bulk_g2s(dst, a_base + (size_t)tile * a_stride + (size_t)jb.a_off * kBlockBytes + (size_t)half * jb.a_blocks * kHalfBlock,
+                       jb.a_blocks * kHalfBlock, bar_full(stage));
+            if (jb.z_blocks > 0)
+              bulk_g2s(dst + 4 * kHalfBlock,
+                       p.dz + ((size_t)tile * p.dz_blocks + jb.z_off) * kBlockBytes + (size_t)half * jb.z_blocks * kHalfBlock,
+                       jb.z_blocks * kHalfBlock, bar_full(stage));
             if (++stage == kWgStages) { stage = 0; phase ^= 1; }
           }
       }
+      if (trp) printf("durf wgrad trace: producer of job 1 part 0: %d tiles, total %lld cyc; waiting for tile flags %lld, for empty stages %lld\n",
+                      my_tiles, clock64() - t_all, w_flag, w_empty);
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer: D[features of A, columns of dZ] += A^T dZ over the 64 samples of a stage (4 x K=16) =====
+    // ===== MMA issuer: D[features of A, columns of dZ] += A^T dZ over the 64 samples of a stage (4 x K=16 per M tile) =====
     if (my_tiles > 0) {      // the whole warp walks the schedule (uniform control flow), one elected lane issues
       constexpr uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
       uint32_t stage = 0, phase = 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      for (int j = my_job; j == my_job; ++j) {
-        const WgradJob jb = p.jobs[j];
-        // one job per CTA: the accumulator is never recycled, no wait on bar_acc_free
-        for (int tile = t_begin; tile < t_end; ++tile)
-          for (int half = 0; half < 2; ++half) {
-            mbar_wait(bar_full(stage), phase);
-            tc_fence_after();
-            if (jb.z_blocks > 0) {
-              const int m_tiles = jb.a_blocks > 2 ? 2 : 1;
-              const uint32_t a_lbo = jb.a_blocks >= 2 ? (uint32_t)(kHalfBlock >> 4) : 0u;    // a single block is read twice (rows 64..127 unused)
-              const uint32_t N = jb.z_blocks * 64;
-              const uint32_t idesc = umma_idesc_mn(128, (int)N);
-              const uint32_t st = sbase + stage * kWgStageBytes;
-              const uint32_t b_lo = (((st + 4 * kHalfBlock) & 0x3FFFF) >> 4) | ((uint32_t)(kHalfBlock >> 4) << 16);
-              for (int mt = 0; mt < m_tiles; ++mt) {
-                const uint32_t a_lo = (((st + mt * 2 * kHalfBlock) & 0x3FFFF) >> 4) | (a_lbo << 16);
-#pragma unroll
-                for (int k16 = 0; k16 < 4; ++k16)
-                  umma_ss_conv(tmem_u + mt * N, a_lo + ((k16 * 2048) >> 4), b_lo + ((k16 * 2048) >> 4), desc_hi, idesc,
-                          (tile == t_begin && half == 0 && k16 == 0) ? 0u : 1u);
-              }
-            }
+      const WgradJob jb = p.jobs[my_job];
+      // one job per CTA: the accumulator is never recycled, no wait on bar_acc_free.  The wait for a stage's operands is
+      // software-pipelined (umma_stage_mn): a blocking wait between two groups of MMAs would drain the tensor queue, which
+      // capped a CTA at ~30 B/cycle of operands - invisible while 148 CTAs saturate HBM, fatal when the kernel shares the GPU
+      // with the data-gradient kernel and runs on a third of the SMs.
+      const uint32_t m2 = jb.a_blocks > 2 ? 1u : 0u;
+      const uint32_t a_lbo = jb.a_blocks >= 2 ? (uint32_t)(kHalfBlock >> 4) : 0u;    // a single block is read twice (rows 64..127 unused)
+      const uint32_t N = jb.z_blocks * 64;
+      const uint32_t idesc = umma_idesc_mn(128, (int)N);
+      mbar_wait(bar_full(0), 0);
+      const bool trm = DURF_TRACE_DETAIL && p.trace_detail && my_job == 1 && p.cta_part[blockIdx.x] == 0;
+      const long long m_all = clock64();
+      for (int tile = t_begin; tile < t_end; tile += t_step)
+        for (int half = 0; half < 2; ++half) {
+          tc_fence_after();
+          const bool last = half == 1 && tile + t_step >= t_end;
+          const uint32_t next_stage = stage + 1 == kWgStages ? 0 : stage + 1;
+          const uint32_t next_phase = stage + 1 == kWgStages ? phase ^ 1 : phase;
+          if (jb.z_blocks > 0) {
+            const uint32_t st = sbase + stage * kWgStageBytes;
+            const uint32_t b_lo = (((st + 4 * kHalfBlock) & 0x3FFFF) >> 4) | ((uint32_t)(kHalfBlock >> 4) << 16);
+            const uint32_t a0_lo = ((st & 0x3FFFF) >> 4) | (a_lbo << 16);
+            const uint32_t a1_lo = (((st + 2 * kHalfBlock) & 0x3FFFF) >> 4) | (a_lbo << 16);
+            umma_stage_mn(tmem_u, tmem_u + N, a0_lo, a1_lo, b_lo, desc_hi, idesc, (tile == t_begin && half == 0) ? 0u : 1u, m2,
+                          bar_empty(stage), bar_full(next_stage), next_phase, last ? 0u : 1u);
+          } else {
             tc_commit_conv(bar_empty(stage));
-            if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+            if (!last) mbar_wait(bar_full(next_stage), next_phase);
           }
-        if (jb.z_blocks > 0) tc_commit_conv(bar_acc_done);
-      }
+          stage = next_stage; phase = next_phase;
+        }
+      if (jb.z_blocks > 0) tc_commit_conv(bar_acc_done);
+      if (trm && lane == 0) printf("durf wgrad trace: MMA warp of job 1 part 0: %d stages in %lld cyc\n", 2 * my_tiles, clock64() - m_all);
     }
   } else if (warp >= 4) {
     // ===== auxiliary warps: bias / narrow-head gradients from the stages in shared memory, then the accumulator read-out.
@@ -180,13 +226,17 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
         const int nvec = jb.extra == 1 ? 1 : (jb.extra == 2 ? 3 : 0);
         const bool do_bias = (jb.db_off >= 0 || jb.extra == 3) && ck < jb.z_blocks * 8;
         const bool do_ex = nvec > 0 && ck < jb.a_blocks * 8;
-        for (int tile = t_begin; tile < t_end; ++tile) {
+        const bool tra = DURF_TRACE_DETAIL && p.trace_detail && my_job == 1 && p.cta_part[blockIdx.x] == 0 && t == 0;
+        long long a_wait = 0, a_work = 0, aq = 0;
+        for (int tile = t_begin; tile < t_end; tile += t_step) {
           const int ray = p.ray_index ? p.ray_index[tile] : tile;
           float tsum[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) tsum[e] = 0.f;
           for (int half = 0; half < 2; ++half) {
+            if (tra) aq = clock64();
             mbar_wait(bar_full(stage), phase);
+            if (tra) { a_wait += clock64() - aq; aq = clock64(); }
             const uint32_t st = sbase + stage * kWgStageBytes;
             if (do_bias) {
               const uint32_t zb = st + (4 + (ck >> 3)) * kHalfBlock;
@@ -222,6 +272,7 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty(stage));
+            if (tra) a_work += clock64() - aq;
             if (++stage == kWgStages) { stage = 0; phase ^= 1; }
           }
 #pragma unroll
@@ -245,6 +296,7 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
             }
           }
         }
+        if (tra) printf("durf wgrad trace: aux thread of job 1 part 0: waiting for full stages %lld cyc, column sums %lld cyc\n", a_wait, a_work);
         // per-thread partial sums -> global gradient (8 row groups x 148 CTAs add into every address)
         if (jb.db_off >= 0 && do_bias) {
 #pragma unroll
@@ -332,7 +384,7 @@ constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 128 + 8 * 128 * 4 + 102
 // Builds the job list for a topology.  Tile records: saved activations = [layer g][W/64 blocks] for the depth+1 trunk /
 // bottleneck layers, then 2 blocks of the condition layer's activation; dz has the same record shape (dz of layer g at
 // the slot of its output activation).
-int mlp_tc_wgrad_launch(cudaStream_t st, const DurfMlpTopology& t, int saved_blocks, const WgradParams& base) {
+int mlp_tc_wgrad_launch(cudaStream_t st, const DurfMlpTopology& t, int saved_blocks, const WgradParams& base, int max_ctas) {
   MlpLayout L(t);
   WgradParams P = base;
   const int KB = t.width / 64, G = t.depth + 2;
@@ -346,6 +398,8 @@ int mlp_tc_wgrad_launch(cudaStream_t st, const DurfMlpTopology& t, int saved_blo
     WgradJob jb{};
     jb.z_off = slot(g); jb.z_blocks = zb; jb.ld = n_out; jb.n_valid = n_out; jb.db_off = (int)L.b_off[layer];
     jb.extra = 0; jb.ex_off = 0; jb.ex_b_off = -1;
+    // dZ of layer g: one increment per epilogue warp (8) and N-half of the data-gradient kernel; dZ_cond: one per warp
+    jb.flag_idx = g; jb.flag_need = (g == G - 1) ? 8 : 8 * (t.width / 128);
     if (g == 0) { jb.a_src = 1; jb.a_off = 0; jb.a_blocks = 1; jb.dw_off = (int)L.w_off[layer]; jb.k_valid = t.in_dim; }
     else {
       // input of trunk layer g / bottleneck = activation g-1 (bottleneck: the last trunk activation); condition layer = bottleneck output
@@ -370,6 +424,7 @@ int mlp_tc_wgrad_launch(cudaStream_t st, const DurfMlpTopology& t, int saved_blo
     WgradJob jr{};
     jr.a_src = 0; jr.a_off = slot(G - 1); jr.a_blocks = t.cond_width / 64; jr.z_blocks = 0; jr.db_off = -1;
     jr.extra = 2; jr.ex_off = (int)L.w_off[t.depth + 3]; jr.ex_b_off = (int)L.b_off[t.depth + 3];
+    jr.flag_idx = -1; jr.flag_need = 0;
     P.jobs[nj++] = jr;
   }
   DURF_REQUIRE(nj <= kMaxJobs, DURF_E_UNSUPPORTED, "durf_mlp_bwd(bf16): too many wgrad jobs (%d)", nj);
@@ -379,6 +434,7 @@ int mlp_tc_wgrad_launch(cudaStream_t st, const DurfMlpTopology& t, int saved_blo
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   sms = sms > kMaxCtas ? kMaxCtas : sms;
+  if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;      // the rest of the GPU runs the data-gradient kernel
   // CTAs per job in proportion to the job's cost per tile, at least one each, never more CTAs than tiles.  Cost model
   // (cycles per tile, measured with DURF_WGRAD_TRACE on 16,384 tiles): 1500 (two ring stages' worth of latency) + 15 per KB
   // streamed + the auxiliary warps' work for the narrow heads (density head 2000, rgb head 2560, view part 1160).
@@ -416,9 +472,21 @@ int mlp_tc_wgrad_launch(cudaStream_t st, const DurfMlpTopology& t, int saved_blo
   cudaError_t e = cudaFuncSetAttribute(mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
   DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_bwd(bf16): smem attribute: %s", cudaGetErrorString(e));
   static long long* trace_buf = nullptr;
-  const bool tracing = getenv("DURF_WGRAD_TRACE") != nullptr;
+  const bool tracing = getenv("DURF_WGRAD_TRACE") != nullptr && atoi(getenv("DURF_WGRAD_TRACE")) == 1;
+  P.trace_detail = (getenv("DURF_WGRAD_TRACE") != nullptr && atoi(getenv("DURF_WGRAD_TRACE")) == 2) ? 1 : 0;
   if (tracing && !trace_buf) cudaMalloc(&trace_buf, kMaxCtas * sizeof(long long));
   P.trace = tracing ? trace_buf : nullptr;
+  if (P.flags && (grid & 1) == 0) {
+    // sharing the GPU with the data-gradient kernel: CTA pairs, so that the two SMs of a TPC run the SAME kernel
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = kWgSmemBytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, mlp_tc_wgrad_kernel, P);
+    DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_bwd(bf16): wgrad launch: %s", cudaGetErrorString(e));
+  } else
   mlp_tc_wgrad_kernel<<<grid, 384, kWgSmemBytes, st>>>(P);
   DURF_CHECK_LAUNCH("durf_mlp_bwd(bf16): wgrad");
   if (tracing) {                                             // debugging aid only: synchronises
@@ -444,11 +512,12 @@ int mlp_tc_saved_blocks(const DurfMlpTopology& t);
 
 int mlp_tc_wgrad_run(cudaStream_t st, const DurfMlpTopology& t, const uint8_t* saved, const uint8_t* feat, const uint8_t* dz,
                      const float* d_raw_rgb, const float* d_raw_density, const float* cond, const int32_t* ray_index,
-                     const int32_t* count, int M, float* d_params) {
+                     const int32_t* count, int M, float* d_params, const int32_t* tile_done, int max_ctas) {
   WgradParams P{};
   P.saved = saved; P.feat = feat; P.dz = dz; P.d_raw_rgb = d_raw_rgb; P.d_raw_density = d_raw_density; P.cond = cond;
   P.ray_index = ray_index; P.count = count; P.M = M; P.cond_dim = t.cond_dim; P.d_params = d_params;
-  return mlp_tc_wgrad_launch(st, t, mlp_tc_saved_blocks(t), P);
+  P.flags = tile_done; P.flag_stride = t.depth + 2;
+  return mlp_tc_wgrad_launch(st, t, mlp_tc_saved_blocks(t), P, max_ctas);
 }
 
 }  // namespace durf

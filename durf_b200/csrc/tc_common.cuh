@@ -4,6 +4,13 @@
 
 #include "common.cuh"
 
+// Per-role cycle counters of the training kernels (DURF_TC_TRACE / DURF_WGRAD_TRACE=2) are compiled in only with
+// `make EXTRA=-DDURF_TRACE_DETAIL=1`: their 64-bit accumulators cost registers in kernels that have none to spare
+// (measured: +4 % on the forward-with-save, +8 % on the data-gradient kernel).
+#ifndef DURF_TRACE_DETAIL
+#define DURF_TRACE_DETAIL 0
+#endif
+
 namespace durf {
 
 constexpr int kTileM = 128;
@@ -179,6 +186,57 @@ __device__ __forceinline__ void umma_kblock_conv(uint32_t d_tmem, uint32_t a, ui
   }
 #undef DURF_KB_WAIT
 #undef DURF_KB_RELEASE
+}
+// One ring stage of the weight-gradient kernel (mlp_tc_wgrad.cu) by a converged warp: 4 (m_tiles == 1) or 8 K=16 MMAs whose
+// MN-major operands advance by 2048 bytes per K step, the commit that frees the stage, and - software-pipelined as in
+// umma_kblock_conv - the wait for the NEXT stage's operands: probed before the MMAs, consumed after them, so the issuing
+// thread never sits in a barrier wait with an empty tensor queue behind it.  d1 / a1_lo: accumulator and A descriptor of the
+// second M tile.
+__device__ __forceinline__ void umma_stage_mn(uint32_t d0, uint32_t d1, uint32_t a0_lo, uint32_t a1_lo, uint32_t b_lo, uint32_t desc_hi,
+                                              uint32_t idesc, uint32_t accumulate_first, uint32_t two_m_tiles, uint32_t bar_release,
+                                              uint32_t bar_next, uint32_t par_next, uint32_t need_next) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e, pacc, ptrue, q, t, m2;\n"
+      ".reg .b64 da, db;\n"
+      ".reg .b32 al, bl, cnt;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 q, [%10], %11;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 pacc, %7, 0;\n"
+      "setp.eq.u32 ptrue, %7, %7;\n"
+      "setp.ne.b32 m2, %8, 0;\n"
+      "and.pred m2, m2, e;\n"
+      "mov.b64 da, {%2, %5};\n mov.b64 db, {%4, %5};\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, pacc;\n"
+      "add.u32 al, %2, 128;\n add.u32 bl, %4, 128;\n mov.b64 da, {al, %5};\n mov.b64 db, {bl, %5};\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, ptrue;\n"
+      "add.u32 al, %2, 256;\n add.u32 bl, %4, 256;\n mov.b64 da, {al, %5};\n mov.b64 db, {bl, %5};\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, ptrue;\n"
+      "add.u32 al, %2, 384;\n add.u32 bl, %4, 384;\n mov.b64 da, {al, %5};\n mov.b64 db, {bl, %5};\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %6, ptrue;\n"
+      "mov.b64 da, {%3, %5};\n mov.b64 db, {%4, %5};\n"
+      "@m2 tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %6, pacc;\n"
+      "add.u32 al, %3, 128;\n add.u32 bl, %4, 128;\n mov.b64 da, {al, %5};\n mov.b64 db, {bl, %5};\n"
+      "@m2 tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %6, ptrue;\n"
+      "add.u32 al, %3, 256;\n add.u32 bl, %4, 256;\n mov.b64 da, {al, %5};\n mov.b64 db, {bl, %5};\n"
+      "@m2 tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %6, ptrue;\n"
+      "add.u32 al, %3, 384;\n add.u32 bl, %4, 384;\n mov.b64 da, {al, %5};\n mov.b64 db, {bl, %5};\n"
+      "@m2 tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %6, ptrue;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n"
+      "setp.eq.u32 t, %12, 0;\n or.pred q, q, t;\n"
+      "mov.u32 cnt, 0;\n"
+      "@q bra LN_DONE;\n"
+      "LN_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%10], %11;\n"
+      "@q bra LN_DONE;\n"
+      "add.u32 cnt, cnt, 1;\n"
+      "setp.lt.u32 t, cnt, 0x4000000;\n"
+      "@t bra LN_WAIT;\n"
+      "trap;\n"
+      "LN_DONE:\n"
+      "}\n" ::"r"(d0), "r"(d1), "r"(a0_lo), "r"(a1_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate_first), "r"(two_m_tiles),
+      "r"(bar_release), "r"(bar_next), "r"(par_next), "r"(need_next)
+      : "memory");
 }
 __device__ __forceinline__ void tc_commit_conv(uint32_t bar) {
   asm volatile(

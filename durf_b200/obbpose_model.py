@@ -67,6 +67,13 @@ class MipNerfModel:
     # IPE in two warps of the kernel, written straight into the shared-memory A operand): no ray-march launch and no
     # 16 KB/ray-level feature image in HBM.  False = separate durf_raymarch_fwd launches (the round-1 path).
     fuse_raymarch: bool = field(default_factory=lambda: os.environ.get('DURF_FUSE_RAYMARCH', '1') != '0')
+    # Opt-in (DURF_BWD_OVERLAP=1): batches of at least `overlap_min_rays` rays run the background network's two backward kernels
+    # CONCURRENTLY on disjoint SMs, the weight-gradient kernel consuming each dZ block out of L2 as soon as the chain has
+    # published it (ops.OverlappedBackward, durf_mlp_bwd_data / durf_mlp_bwd_weights).  Result-identical and tested, but on a
+    # B200 it is not faster than running them back to back (both kernels are bound per SM, not by HBM, so
+    # splitting the SMs between them only moves the time around): off by default.
+    overlap_backward: bool = field(default_factory=lambda: os.environ.get('DURF_BWD_OVERLAP', '0') == '1')
+    overlap_min_rays: int = 2048
 
     # -- topology helpers ------------------------------------------------------------------------------
     def bg_topology(self):
@@ -243,6 +250,11 @@ class MipNerfModel:
         done = on_network_done or (lambda name: None)
         prec = L.PREC_BF16 if self.precision == 'bf16' else L.PREC_FP32
         raw_grads = []
+        # opt-in: the background network's dZ chain and its weight-gradient kernel run concurrently on disjoint SMs
+        # (ops.OverlappedBackward); the weight kernel of level 0 keeps going under the chain of level 1.
+        overlap = None
+        if prec == L.PREC_BF16 and self.overlap_backward and B >= self.overlap_min_rays:
+            overlap = ops.OverlappedBackward()
         for lvl, g in zip(ctx['levels'], level_grads):
             g_rgb, g_den, g_dirs = ops.composite_bwd(lvl['raw_rgb'], lvl['raw_density'], lvl['t_vals'], fe['dirs_s'],
                                                      g['comp_rgb'], g['depth'], g['weights'], white_bkgd=ctx['white_bkgd'],
@@ -251,8 +263,14 @@ class MipNerfModel:
             raw_grads.append((g_rgb, g_den))
             if pose_opt:
                 d_ds += g_dirs * (fe['nhit'] > 0).float()[:, None]            # only object rays carry pose-dependent dirs
-            ops.mlp_bwd(bt, lvl['feat_bg'], viewenc, variables.blob('MLP_0'), lvl['saved_bg'], g_rgb, g_den,
-                        variables.blob_of(d_flat, 'MLP_0'), M=B, N=N, precision=prec, packed=variables.packed.get('MLP_0'))
+            if overlap is not None:
+                overlap(bt, lvl['feat_bg'], viewenc, variables.blob('MLP_0'), lvl['saved_bg'], g_rgb, g_den,
+                        variables.blob_of(d_flat, 'MLP_0'), M=B, N=N, packed=variables.packed.get('MLP_0'))
+            else:
+                ops.mlp_bwd(bt, lvl['feat_bg'], viewenc, variables.blob('MLP_0'), lvl['saved_bg'], g_rgb, g_den,
+                            variables.blob_of(d_flat, 'MLP_0'), M=B, N=N, precision=prec, packed=variables.packed.get('MLP_0'))
+        if overlap is not None:
+            overlap.join()
         done('MLP_0')
         for k in range(K if self.dynamics else 0):
             for lvl, (g_rgb, g_den) in zip(ctx['levels'], raw_grads):

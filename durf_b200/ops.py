@@ -6,6 +6,7 @@ This is the lowest host layer; `mip.py`, `mip360.py`, `box_helpers.py`, `math.py
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -295,9 +296,74 @@ def mlp_bwd(topo, features, cond, blob, saved, d_raw_rgb, d_raw_density, d_blob,
     dfeat = torch.empty(M * N, t.in_dim, device=dev) if want_d_features else None
     a = _mlp_args(t, precision, M, N, features, f32(cond), f32(blob), packed, ray_index, count, False, d_raw_rgb, d_raw_density,
                   saved, ws)
+    _poison(ws)
+    cap = int(os.environ.get('DURF_WGRAD_CTAS', '0'))
+    if cap > 0 and precision == L.PREC_BF16:
+        # diagnostic: the serial backward with the weight-gradient kernel on `cap` CTAs (the partition of the tiles over
+        # accumulators that OverlappedBackward uses), so that the two can be compared reduction for reduction
+        g_rgb, g_den = f32(d_raw_rgb), f32(d_raw_density)
+        check(lib.durf_mlp_bwd_data(stream_ptr(), C.byref(a), ptr(g_rgb), ptr(g_den), ptr(dfeat), None, 0), "durf_mlp_bwd_data")
+        check(lib.durf_mlp_bwd_weights(stream_ptr(), C.byref(a), ptr(g_rgb), ptr(g_den), ptr(d_blob), None, cap), "durf_mlp_bwd_weights")
+        return dfeat
     check(lib.durf_mlp_bwd(stream_ptr(), C.byref(a), ptr(f32(d_raw_rgb)), ptr(f32(d_raw_density)), ptr(d_blob), ptr(dfeat)),
           "durf_mlp_bwd")
     return dfeat
+
+
+def _poison(ws: torch.Tensor) -> None:
+    """DURF_BWD_POISON=1 (tests): fill the dZ workspace with NaN patterns, so that a block consumed before it was produced
+    shows up as a non-finite gradient instead of as the (identical) stale data of the previous call."""
+    if os.environ.get('DURF_BWD_POISON', '0') == '1':
+        ws.fill_(0xFF)
+
+
+class OverlappedBackward:
+    """The tensor-core backward of one large network with its two kernels running CONCURRENTLY: the dZ chain
+    (durf_mlp_bwd_data) on the current stream with `data_ctas` CTAs, the weight gradients (durf_mlp_bwd_weights) on a side
+    stream with the remaining SMs, consuming every dZ block out of L2 as soon as the chain has published it
+    (tile_done counters, include/durf_b200.h).  Several calls may be queued (one per level); `join()` makes the current
+    stream wait for the side stream and releases the buffers that were kept alive for it."""
+
+    _side = {}
+
+    def __init__(self, data_ctas: Optional[int] = None):
+        dev = torch.cuda.current_device()
+        if dev not in OverlappedBackward._side:
+            OverlappedBackward._side[dev] = torch.cuda.Stream(device=dev)
+        self.side = OverlappedBackward._side[dev]
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        if data_ctas is None:
+            data_ctas = int(os.environ.get('DURF_BWD_DATA_CTAS', str(round(sms * 0.65))))
+        self.data_ctas = max(1, min(sms - 1, data_ctas))
+        self.weight_ctas = sms - self.data_ctas
+        self.keep = []
+
+    def __call__(self, topo, features, cond, blob, saved, d_raw_rgb, d_raw_density, d_blob, *, M: int, N: int, packed):
+        t = topology(topo)
+        dev = _dev(features)
+        lib = L.load()
+        prec = L.PREC_BF16
+        ws = torch.empty(max(int(lib.durf_mlp_workspace_bytes(C.byref(t), prec, M, N, 1)), 16), device=dev, dtype=torch.uint8)
+        flags = torch.zeros(max(int(lib.durf_mlp_bwd_flags_bytes(C.byref(t), M)) // 4, 1), device=dev, dtype=torch.int32)
+        _poison(ws)
+        g_rgb, g_den = f32(d_raw_rgb), f32(d_raw_density)
+        a = _mlp_args(t, prec, M, N, features, f32(cond), f32(blob), packed, None, None, False, g_rgb, g_den, saved, ws)
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)                   # the counters are zero, the upstream gradients written
+        check(lib.durf_mlp_bwd_data(cur.cuda_stream, C.byref(a), ptr(g_rgb), ptr(g_den), None, ptr(flags), self.data_ctas),
+              "durf_mlp_bwd_data")
+        if os.environ.get('DURF_BWD_SERIALIZE', '0') == '1':      # diagnosis: same launches, one stream
+            check(lib.durf_mlp_bwd_weights(cur.cuda_stream, C.byref(a), ptr(g_rgb), ptr(g_den), ptr(d_blob), ptr(flags),
+                                           self.weight_ctas), "durf_mlp_bwd_weights")
+        else:
+            with torch.cuda.stream(self.side):
+                check(lib.durf_mlp_bwd_weights(self.side.cuda_stream, C.byref(a), ptr(g_rgb), ptr(g_den), ptr(d_blob), ptr(flags),
+                                               self.weight_ctas), "durf_mlp_bwd_weights")
+        self.keep.append((ws, flags, g_rgb, g_den, a))
+
+    def join(self) -> None:
+        torch.cuda.current_stream().wait_stream(self.side)
+        self.keep.clear()
 
 
 # ---- K3 ---------------------------------------------------------------------------------------------

@@ -189,7 +189,9 @@ typedef struct DurfMlpArgs {
   float* raw_rgb;           /* [B,N,3] */
   float* raw_density;       /* [B,N] */
   void* saved;              /* [opt] kept for the backward pass (durf_mlp_saved_bytes): FP32 the layer outputs; BF16 every
-                               layer's bf16 activations as tile images followed by the trunk layers' 1-bit ReLU masks.  The
+                               layer's bf16 activations as SWIZZLE_128B block images, per layer ordered [sample half][64-column
+                               block][64 rows], followed by the trunk layers' 1-bit ReLU masks (an opaque record: only
+                               durf_mlp_bwd* read it).  The
                                backward call must pass the same buffer with the same M. */
   void* workspace;
   size_t workspace_bytes;
@@ -212,6 +214,22 @@ int durf_mlp_fwd(durf_stream_t stream, const DurfMlpArgs* args);
  * caller zeroes) and [opt] d_features fp32 [M*N,in_dim] (needed only for the pose gradient). */
 int durf_mlp_bwd(durf_stream_t stream, const DurfMlpArgs* args, const float* d_raw_rgb,
                  const float* d_raw_density, float* d_params, float* d_features);
+
+/* The same backward (DURF_PREC_BF16 only) as its two kernels, for callers that run them CONCURRENTLY on two streams:
+ * durf_mlp_bwd_data walks the dZ chain (jax.grad through obbpose_model.py:326-353 w.r.t. the activations) and writes
+ * every layer's dZ into args->workspace; durf_mlp_bwd_weights forms dW = A^T dZ, db (ACCUMULATED into d_params) from
+ * those records.  `tile_done` is an int32 array of durf_mlp_bwd_flags_bytes(topo, M) bytes that the caller ZEROES
+ * (stream-ordered before both launches): the data kernel release-increments tile_done[tile][layer] as each dZ block
+ * becomes complete in global memory, the weight kernel acquires it before fetching the block, so the dZ records are
+ * consumed out of L2 while the chain is still running.  `max_ctas` caps each kernel's grid (0 = every SM): the two
+ * caps must add up to at most the SM count, and the data kernel must be able to start (it never waits for the weight
+ * kernel; the weight kernel traps, never hangs, if a tile does not arrive within ~2 s).  With tile_done = NULL the
+ * weight kernel must be stream-ordered after the data kernel (that is what durf_mlp_bwd does). */
+size_t durf_mlp_bwd_flags_bytes(const DurfMlpTopology* topo, int32_t M);
+int durf_mlp_bwd_data(durf_stream_t stream, const DurfMlpArgs* args, const float* d_raw_rgb,
+                      const float* d_raw_density, float* d_features, int32_t* tile_done, int32_t max_ctas);
+int durf_mlp_bwd_weights(durf_stream_t stream, const DurfMlpArgs* args, const float* d_raw_rgb,
+                         const float* d_raw_density, float* d_params, const int32_t* tile_done, int32_t max_ctas);
 
 /* ---- K3: activations + alpha compositing ---------------------------------------------------- */
 typedef struct DurfCompositeArgs {

@@ -172,6 +172,52 @@ def test_graph_captured_step_replays_like_eager(pose_opt):
     assert abs(float(stats_g['loss']) - float(stats_e['loss'])) <= 1e-4 * max(1.0, abs(float(stats_e['loss'])))
 
 
+@pytest.mark.parametrize("B", [300, 1500])
+def test_overlapped_backward_equals_the_serial_backward(B, monkeypatch):
+    """ops.OverlappedBackward (the dZ chain and the weight-gradient kernel of the background network on disjoint SMs, dZ
+    blocks handed over through the tile_done counters) gives the gradient of the serial durf_mlp_bwd: same kernels, same
+    operands, only the order of the fp32 reductions differs (<= 1e-5 relative, against the run-to-run noise of the serial
+    path).  B = 300 leaves most weight-gradient CTAs waiting for tiles; B = 1500 spans several waves of the chain.  Also
+    inside a captured CUDA graph (fork / join of the side stream)."""
+    from durf_b200.train import TrainState, train_step, GraphedTrainStep
+    from durf_b200.utils import Config
+    sc, mk, rng = _train_inputs(B, 2, seed=97)
+    config = Config()
+
+    from durf_b200 import ops
+    wcap = ops.OverlappedBackward().weight_ctas
+
+    def grad(overlap):
+        model = _model(precision='bf16', overlap_backward=overlap, overlap_min_rays=0)
+        st = TrainState.create(H.cuda_variables(sc, model))
+        _, stats = train_step(model, config, rng, st, mk(1), lr=1e-3, eps=3.0, alpha=10.0)
+        torch.cuda.synchronize()
+        return stats['grad'].double().clone(), stats['loss'].clone()
+    # the serial reference runs its weight-gradient kernel on the same number of CTAs (same split of the tiles over fp32
+    # accumulators); NaN-poisoned dZ workspaces turn any block read before it was written into a non-finite gradient
+    monkeypatch.setenv('DURF_BWD_POISON', '1')
+    monkeypatch.setenv('DURF_WGRAD_CTAS', str(wcap))
+    g_serial, l_serial = grad(False)
+    g_serial2, _ = grad(False)
+    monkeypatch.delenv('DURF_WGRAD_CTAS')
+    g_full, _ = grad(False)                        # all SMs: a different partition, fp32 summation-order noise only
+    g_over, l_over = grad(True)
+    assert float((g_serial - g_full).norm() / g_serial.norm()) <= 2e-4
+    noise = float((g_serial - g_serial2).norm() / g_serial.norm())
+    rel = float((g_serial - g_over).norm() / g_serial.norm())
+    assert float(g_serial.norm()) > 0 and torch.isfinite(g_over).all()
+    assert rel <= max(1e-5, 3.0 * noise), f"overlapped vs serial backward: {rel:.3e} (serial vs serial: {noise:.3e})"
+    assert torch.equal(l_serial, l_over)
+    # captured: the fork / join of the side stream becomes two parallel branches of the graph
+    model_g = _model(precision='bf16', overlap_backward=True, overlap_min_rays=0)
+    st_g = TrainState.create(H.cuda_variables(sc, model_g))
+    step = GraphedTrainStep(model_g, config, st_g, B, 2)
+    stats_g = step(mk(1), 1e-3, 3.0, 10.0, rng=rng)
+    torch.cuda.synchronize()
+    rel_g = float((g_serial - stats_g['grad'].double()).norm() / g_serial.norm())
+    assert rel_g <= max(1e-5, 3.0 * noise), f"graph-captured overlapped backward: {rel_g:.3e}"
+
+
 def test_loss_value_is_bit_reproducible_and_step_has_no_host_sync():
     """The loss reduction is deterministic (fixed-order block partials instead of float atomics), and a bf16 train step issues
     no device->host read (checked with torch's sync debug mode)."""
