@@ -88,10 +88,10 @@ extern "C" size_t durf_mlp_workspace_bytes(const DurfMlpTopology* topo, int32_t 
 extern "C" size_t durf_mlp_saved_bytes(const DurfMlpTopology* topo, int32_t precision, int32_t M, int32_t N) {
   if (!topology_ok(topo) || M < 0 || N < 1) return 0;
   if (precision == DURF_PREC_FP32) return sizeof(float) * mlp_fp32_saved_floats(*topo, (int64_t)M * N);
-  // bf16 activations of every layer as tile images, then the 1-bit ReLU masks of the trunk layers (4 bytes per row and
+  // bf16 activations of every layer as tile images, then the 1-bit ReLU masks of the trunk layers and the condition layer (4 bytes per row and
   // 32-column group)
   return mlp_tc_bwd_supported(*topo)
-             ? (size_t)M * mlp_tc_saved_blocks(*topo) * 16384 + (size_t)M * topo->depth * (topo->width / 32) * 128 * 4
+             ? (size_t)M * mlp_tc_saved_blocks(*topo) * 16384 + (size_t)M * (topo->depth + 1) * (topo->width / 32) * 128 * 4
              : 0;
 }
 

@@ -81,7 +81,8 @@ struct TcParams {
   const int32_t* count;
   uint8_t* saved;            // [opt] training: every layer's bf16 activations as tile images (see mlp_tc_saved_bytes)
   int saved_blocks_per_tile;
-  uint32_t* masks;           // [opt] training: 1-bit ReLU masks of the trunk layers, [tile][layer][32-column group][row] words
+  uint32_t* masks;           // [opt] training: 1-bit ReLU masks of the trunk layers and (layer index `depth`) the condition layer,
+                             // [tile][depth + 1][W / 32 column groups][row] words
   int M;
   int accumulate;
   float* raw_rgb;
@@ -568,7 +569,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
                   asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(gt) : "r"(pk[i][k]), "r"(0u));
                   mw |= gt & (0x80008000u >> k);
                 }
-                if (valid) p.masks[(((size_t)tile * p.depth + g) * (W / 32) + ((col0 + i * 32) >> 5)) * 128 + row] = mw;
+                if (valid) p.masks[(((size_t)tile * (p.depth + 1) + (kind == 3 ? p.depth : g)) * (W / 32) + ((col0 + i * 32) >> 5)) * 128 + row] = mw;
               }
 #pragma unroll
               for (int q4 = 0; q4 < 4; ++q4)
@@ -688,7 +689,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
                 rgb[2] = fmaf(a0, w2.x, rgb[2]); rgb[2] = fmaf(a1, w2.y, rgb[2]); rgb[2] = fmaf(a2, w2.z, rgb[2]); rgb[2] = fmaf(a3, w2.w, rgb[2]);
                 if (SAVE) { pkc[i][2 * j] = cvt_bf16x2(a0, a1); pkc[i][2 * j + 1] = cvt_bf16x2(a2, a3); }
               }
-            if constexpr (SAVE) save_piece(pkc, false);    // the condition layer's activation (wgrad operand; its mask is read from it)
+            if constexpr (SAVE) save_piece(pkc, true);     // the condition layer's activation (wgrad operand) and its 1-bit mask (mask layer `depth`)
           }
         }
       }

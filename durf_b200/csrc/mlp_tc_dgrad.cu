@@ -83,6 +83,7 @@ struct DgCfg {
   static constexpr int OFF_MISC = OFF_WRGB + 128 * 4 * 4;
   static constexpr int MISC_BYTES = 2048;                             // tmem ptr + barriers (256 B) | publisher mailboxes
   static constexpr int OFF_MAIL = OFF_MISC + 256;                     // [8] heads (128 B) | [8][kMailSlots] counter offsets
+  static constexpr int OFF_EPI = OFF_MAIL + 128 + 8 * kMailSlots * 4;  // [kDgMaxStages + 4] stage table of the epilogue warps
   static constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -148,15 +149,28 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
   auto bar_acc_full = [&](int h) { return bar0 + 8 * (16 + h); };
   auto bar_a_ready = [&](int h) { return bar0 + 8 * (18 + h); };
   const uint32_t bar_p_ready = bar0 + 8 * 20;
-  static_assert(16 + 8 * 21 <= 256 && 256 + 128 + 8 * kMailSlots * 4 <= C::MISC_BYTES, "barrier area + mailboxes");
+  static_assert(16 + 8 * 21 <= 256 && 256 + 128 + 8 * kMailSlots * 4 + (kDgMaxStages + 4) * 4 <= C::MISC_BYTES, "barrier area + mailboxes + stage table");
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int h = 0; h < 2; ++h) { mbar_init(bar_acc_full(h), 1); mbar_init(bar_a_ready(h), 256); }
-    mbar_init(bar_p_ready, 256);
+    for (int h = 0; h < 2; ++h) { mbar_init(bar_acc_full(h), 1); mbar_init(bar_a_ready(h), 8); }   // one arrival per epilogue warp
+    mbar_init(bar_p_ready, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 32) reinterpret_cast<uint32_t*>(smem + C::OFF_MAIL)[threadIdx.x] = 0;      // mailbox heads
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + kDgMaxStages + 4) {
+    // what the epilogue warps need of a stage, one word (a constant-bank lookup with a run-time index costs them ~250 cycles
+    // per epilogue): kind 0-1 | n_halves 2-3 | last_part 4 | feeds_next 5 | o_sel 6 | to_skip 7 | out_slot 8-15 | mask layer 16-20
+    const int si = threadIdx.x - 32;
+    uint32_t w = 0;
+    if (si < p.n_stages) {
+      const DgStage& S = p.st[si];
+      const int mg = (S.kind == 1 || S.kind == 2) ? S.mask_slot / C::KB : 31;
+      w = (uint32_t)S.kind | ((uint32_t)S.n_halves << 2) | (S.last_part ? 16u : 0u) | (S.o_sel >= 0 ? 32u : 0u) |
+          ((S.o_sel > 0 ? 1u : 0u) << 6) | (S.to_skip ? 128u : 0u) | ((uint32_t)S.out_slot << 8) | ((uint32_t)mg << 16);
+    }
+    reinterpret_cast<uint32_t*>(smem + C::OFF_EPI)[si] = w;
+  }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(C::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -309,85 +323,106 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
     int pq[kPubDepth];
 #pragma unroll
     for (int i = 0; i < kPubDepth; ++i) pq[i] = -1;
-    const bool tr = DURF_TRACE_DETAIL && p.trace && blockIdx.x == 0 && threadIdx.x == 128;
-    long long e_begin = clock64(), e_pro = 0, e_acc = 0, e_wg = 0, e_work = 0, e_pub = 0, eq = 0, e_fence = 0, e_issue = 0, e_mask = 0;
+    const uint32_t* s_epi = reinterpret_cast<const uint32_t*>(smem + C::OFF_EPI);      // stage table, see epi_word
+    const uint32_t my_out = sbase + C::OFF_OUT + ((warp - 4) << 12);
+    const uint32_t row_off = (lane >> 3) * 1024 + (lane & 7) * 128, r7 = lane & 7;
+    // this warp's 4 KB piece inside a layer record [sample half][64-column block][64 rows x 128 B]: `nb` blocks per half
+    const uint32_t piece_w = (uint32_t)(q >> 1) * (C::KB * 8192) + ch * 8192 + (q & 1) * 4096;      // + h * 16384: a W-wide layer
+    const uint32_t piece_c = (uint32_t)(q >> 1) * (2 * 8192) + ch * 8192 + (q & 1) * 4096;          // the condition layer (2 blocks)
+    const size_t mask_tile_words = (size_t)(p.depth + 1) * (W / 32) * 128;
+    // The staging piece is free once the previous bulk store has read it; with tile_done counters the oldest queued piece is
+    // handed to the publisher once it is complete in global memory.
+    auto staging_acquire = [&](int flag_off) {
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (p.flags) {
+          asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPubDepth - 1) : "memory");
+          if (pq[0] >= 0) mail_push(pq[0]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i + 1 < kPubDepth; ++i) pq[i] = pq[i + 1];
+      pq[kPubDepth - 1] = p.flags ? flag_off : -1;
+      __syncwarp();
+    };
+    auto staging_store = [&](uint8_t* gdst) {      // generic-proxy writes of the whole warp -> one 4 KB bulk store
+      __syncwarp();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(gdst), "r"(my_out) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
+    // inputs of a tile's prologue (upstream gradients of this row, mask words of the condition layer): fetched while the
+    // previous tile's last stage runs, so that no global-memory latency sits at the tile boundary
+    float pre_g[4] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t pre_mw[2] = {0u, 0u};
+    auto prefetch_tile = [&](int t2) {
+      const int ray2 = p.ray_index ? p.ray_index[t2] : t2;
+      const float* g3 = p.d_raw_rgb + ((size_t)ray2 * kTileM + row) * 3;
+      pre_g[0] = __ldg(g3); pre_g[1] = __ldg(g3 + 1); pre_g[2] = __ldg(g3 + 2);
+      pre_g[3] = __ldg(p.d_raw_density + (size_t)ray2 * kTileM + row);
+      const uint32_t* src = p.masks + (size_t)t2 * mask_tile_words + ((size_t)p.depth * (W / 32) + ch * 2) * 128 + row;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(pre_mw[i]) : "l"(src + i * 128));
+    };
+    if ((int)blockIdx.x < num_tiles) prefetch_tile(blockIdx.x);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      if (tr) eq = clock64();
-      const int ray = p.ray_index ? p.ray_index[tile] : tile;
-      const uint8_t* sv = p.saved + (size_t)tile * p.saved_blocks * kBlockBytes;
       uint8_t* dzt = p.dz + (size_t)tile * p.saved_blocks * kBlockBytes;
-      // ---- prologue: dZ_cond[row, c] = (sum_j d_rgb[row, j] W_rgb[c, j]) * [cond_act[row, c] > 0], c in this warp's 64 columns
+      const uint32_t* mrow = p.masks + (size_t)tile * mask_tile_words + (size_t)(ch * 2) * 128 + row;
+      const float gden = pre_g[3];
+      // ---- prologue: dZ_cond[row, c] = (sum_j d_rgb[row, j] W_rgb[c, j]) * [cond_act[row, c] > 0], c in this warp's 64 columns;
+      // the ReLU mask is the forward's 1-bit word, the row goes to TMEM (A operand of stage 0) and, through the staging piece,
+      // to the dZ record (B operand of the weight-gradient kernel)
       {
-        const float* g3 = p.d_raw_rgb + ((size_t)ray * kTileM + row) * 3;
-        const float g0 = g3[0], g1 = g3[1], g2 = g3[2];
-        const int c0 = ch * 64;                                   // columns [c0, c0 + 64) = block ch of the condition slot
-        // layer records are [sample half][64-column block][64 rows x 128 B] (see mlp_tc.cu, save_piece); the condition layer has
-        // two blocks
-        const size_t cond_off = (size_t)p.cond_slot * kBlockBytes + (size_t)(row >> 6) * (2 * 8192) + ch * 8192;
-        const uint8_t* act = sv + cond_off;
-        uint8_t* out = dzt + cond_off;
-        const uint32_t row64 = row & 63;
+        const float g0 = pre_g[0], g1 = pre_g[1], g2 = pre_g[2];
+        const uint32_t mwc[2] = {pre_mw[0], pre_mw[1]};
+        const int c0 = ch * 64;
+        staging_acquire(tile * p.flag_stride + p.cond_slot / C::KB);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           uint32_t pk[16];
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            const uint4 a4 = *reinterpret_cast<const uint4*>(act + sw128_offset(row64, i * 4 + c8));
-            const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = c0 + i * 32 + c8 * 8 + 2 * e;
-              const float4 w0 = lds128_volatile(sbase + C::OFF_WRGB + c * 16), w1 = lds128_volatile(sbase + C::OFF_WRGB + (c + 1) * 16);
-              const float v0 = fmaf(g2, w0.z, fmaf(g1, w0.y, g0 * w0.x)), v1 = fmaf(g2, w1.z, fmaf(g1, w1.y, g0 * w1.x));
-              pk[c8 * 4 + e] = mask_pair(cvt_bf16x2(v0, v1), aw[e]);
-            }
-            *reinterpret_cast<uint4*>(out + sw128_offset(row64, i * 4 + c8)) =
-                make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+          for (int e = 0; e < 16; ++e) {
+            const int c = c0 + i * 32 + 2 * e;
+            const float4 w0 = lds128(sbase + C::OFF_WRGB + c * 16), w1 = lds128(sbase + C::OFF_WRGB + (c + 1) * 16);
+            const float v0 = fmaf(g2, w0.z, fmaf(g1, w0.y, g0 * w0.x)), v1 = fmaf(g2, w1.z, fmaf(g1, w1.y, g0 * w1.x));
+            pk[e] = mask_pair_bits(cvt_bf16x2(v0, v1), mwc[i], e);
           }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_out + row_off + (((uint32_t)(i * 4 + q4) ^ r7) << 4)),
+                         "r"(pk[4 * q4]), "r"(pk[4 * q4 + 1]), "r"(pk[4 * q4 + 2]), "r"(pk[4 * q4 + 3]) : "memory");
           tmem_st16(t_lane + C::ACT_COL + (c0 + i * 32) / 2, pk);     // A operand of stage 0 = activation buffer 0
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(bar_p_ready);
-        if (p.flags) {             // dZ_cond went out with generic stores: fence each thread's, then one increment per warp
-          __threadfence();
-          __syncwarp();
-          if (lane == 0) mail_push(tile * p.flag_stride + p.cond_slot / C::KB);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p_ready);
+        staging_store(dzt + (size_t)p.cond_slot * kBlockBytes + piece_c);
       }
-      if (tr) e_pro += clock64() - eq;
-      const float gden = p.d_raw_density[(size_t)ray * kTileM + row];
-      const uint32_t my_out = sbase + C::OFF_OUT + ((warp - 4) << 12);
-      const uint32_t row_off = (lane >> 3) * 1024 + (lane & 7) * 128, r7 = lane & 7;
-      // the warp's 32 rows x 64 columns of a block image are a contiguous 4 KB piece: dZ leaves by one bulk store per epilogue;
-      // the ReLU masks are the forward's 1-bit words (one 4-byte load per thread and 32-column group, issued one epilogue
-      // ahead), so HBM traffic never blocks the epilogue
-      auto fetch_mask = [&](int s2, int h2) {
-        const int g2 = p.st[s2].mask_slot / C::KB;       // trunk layer whose activation gates this stage's output
-        const uint32_t* src = p.masks + (((size_t)tile * p.depth + g2) * (W / 32) + ((h2 * 128 + ch * 64) >> 5)) * 128 + row;
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-          asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(mw_next[i]) : "l"(src + i * 128));
-      };
+      uint32_t ew = s_epi[0];
       for (int s = 0; s < p.n_stages; ++s) {
-        const DgStage S = p.st[s];
-        if (!S.last_part) continue;                    // entries that only accumulate have no epilogue
-        const uint32_t o_buf = t_lane + C::ACT_COL + (S.o_sel < 0 ? 0 : S.o_sel) * (W / 2);
-        const bool feeds_next = S.o_sel >= 0;
-        for (int h = 0; h < S.n_halves; ++h) {
+        const uint32_t w = ew;
+        ew = s_epi[s + 1];                             // the next stage's entry (table is padded): off the post-barrier path
+        if (s + 1 == p.n_stages && tile + (int)gridDim.x < num_tiles) prefetch_tile(tile + (int)gridDim.x);
+        if (!(w & 16u)) continue;                      // entries that only accumulate have no epilogue
+        const int kind = w & 3, n_halves = (w >> 2) & 3, out_slot = (w >> 8) & 0xFF;
+        const bool feeds_next = (w & 32u) != 0, to_skip = (w & 128u) != 0;
+        const uint32_t o_buf = t_lane + C::ACT_COL + ((w >> 6) & 1u) * (W / 2);
+        for (int h = 0; h < n_halves; ++h) {
           const int col0 = h * 128 + ch * 64;
-          if (tr) eq = clock64();
           mbar_wait(bar_acc_full(h), af_par[h]); af_par[h] ^= 1;
-          if (tr) { e_acc += clock64() - eq; eq = clock64(); }
           tc_fence_after();
-          if (S.kind == 3) {
+          if (kind == 3) {
             // input gradient: 64 accumulator columns (the in_dim features), fp32 rows straight to d_features
             uint32_t v[32];
             tmem_ld32_issue(t_lane + C::ACC_COL + ch * 32, v);
             tmem_ld_wait();
             tmem_ld_pin(v);
             tc_fence_before();
-            mbar_arrive(bar_a_ready(0));               // accumulators drained
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a_ready(0));               // accumulators drained
             float* dx = p.d_features + ((size_t)tile * kTileM + row) * p.in_dim;
 #pragma unroll
             for (int e = 0; e < 32; ++e)
@@ -396,56 +431,42 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
           }
           uint32_t v[32];
           tmem_ld32_issue(t_lane + C::ACC_COL + col0, v);
-          uint32_t mw[2] = {mw_next[0], mw_next[1]};
-          if (tr) { asm volatile("" : "+r"(mw[0]), "+r"(mw[1])); e_mask += clock64() - eq; eq = clock64(); }
-          if (lane == 0) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // previous dZ piece was read out
-            if (p.flags) {
-              asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPubDepth - 1) : "memory");     // the oldest queued piece is in HBM / L2
-              if (pq[0] >= 0) mail_push(pq[0]);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i + 1 < kPubDepth; ++i) pq[i] = pq[i + 1];
-          pq[kPubDepth - 1] = p.flags ? tile * p.flag_stride + S.out_slot / C::KB : -1;
-          __syncwarp();
-          if (tr) { e_wg += clock64() - eq; eq = clock64(); }
+          const uint32_t mw[2] = {mw_next[0], mw_next[1]};
+          staging_acquire(tile * p.flag_stride + out_slot / C::KB);
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             tmem_ld_wait();
             tmem_ld_pin(v);
             uint32_t pk[16];
             const uint32_t wden_addr = sbase + C::OFF_WDEN + (col0 + i * 32) * 4;
-            if (S.kind == 0) dg_pack<0>(v, mw[i], gden, wden_addr, my_out + row_off, r7, i * 4, pk);
-            else if (S.kind == 1) dg_pack<1>(v, mw[i], gden, wden_addr, my_out + row_off, r7, i * 4, pk);
+            if (kind == 0) dg_pack<0>(v, mw[i], gden, wden_addr, my_out + row_off, r7, i * 4, pk);
+            else if (kind == 1) dg_pack<1>(v, mw[i], gden, wden_addr, my_out + row_off, r7, i * 4, pk);
             else dg_pack<2>(v, mw[i], gden, wden_addr, my_out + row_off, r7, i * 4, pk);
             if (i == 0) tmem_ld32_issue(t_lane + C::ACC_COL + col0 + 32, v);
             if (feeds_next) tmem_st16(o_buf + (col0 + i * 32) / 2, pk);
-            if (W == 128 && S.to_skip) tmem_st16(t_lane + C::ACT_COL + 2 * (W / 2) + (col0 + i * 32) / 2, pk);
+            if (W == 128 && to_skip) tmem_st16(t_lane + C::ACT_COL + 2 * (W / 2) + (col0 + i * 32) / 2, pk);
           }
-          if (feeds_next || S.to_skip) tmem_st_wait();
+          if (feeds_next || to_skip) tmem_st_wait();
           tc_fence_before();
-          mbar_arrive(bar_a_ready(h));     // next stage's A operand half is in TMEM (last stage: accumulators drained)
-          if (tr) { e_work += clock64() - eq; eq = clock64(); }
-          // off the critical path: publish the dZ piece, fetch the next epilogue's mask piece
           __syncwarp();
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          if (tr) { e_fence += clock64() - eq; eq = clock64(); }
-          if (lane == 0) {
-            uint8_t* gdst = dzt + (size_t)S.out_slot * kBlockBytes + (size_t)(q >> 1) * (C::KB * 8192) + (col0 >> 6) * 8192 + (q & 1) * 4096;
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 4096;" ::"l"(gdst), "r"(my_out) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (lane == 0) mbar_arrive(bar_a_ready(h));     // next stage's A operand half is in TMEM (last stage: accumulators drained)
+          // off the critical path: the dZ piece leaves by one bulk store, the next masked epilogue's mask words are requested
+          staging_store(dzt + (size_t)out_slot * kBlockBytes + h * 16384 + piece_w);
+          uint32_t wn = w;
+          int h2 = h + 1;
+          if (h2 >= n_halves) {                          // the next entry with an epilogue (entries are padded with zeros)
+            h2 = 0; wn = ew;
+            for (int s2 = s + 2; !(wn & 16u) && s2 <= p.n_stages; ++s2) wn = s_epi[s2];
           }
-          if (tr) { e_issue += clock64() - eq; eq = clock64(); }
-          int h2 = h + 1, s2 = s;
-          if (h2 >= S.n_halves) { h2 = 0; ++s2; while (s2 < p.n_stages && !p.st[s2].last_part) ++s2; }    // next entry with an epilogue
-          if (s2 < p.n_stages && (p.st[s2].kind == 1 || p.st[s2].kind == 2)) fetch_mask(s2, h2);
-          if (tr) e_pub += clock64() - eq;
+          const int mg = (wn >> 16) & 31;                // trunk layer whose ReLU mask gates that epilogue's output (31: none)
+          if ((wn & 16u) && mg != 31) {
+            const uint32_t* src = mrow + ((size_t)mg * (W / 32) + h2 * 4) * 128;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(mw_next[i]) : "l"(src + i * 128));
+          }
         }
       }
     }
-    if (tr) printf("durf dgrad trace: epilogue thread: total %lld cyc; prologue %lld, waiting acc_full %lld, mask words arrive %lld, bulk wait_group %lld, ld+pack+st+arrive %lld, fence %lld, bulk-store issue %lld, next-stage lookup + mask fetch %lld\n",
-                   clock64() - e_begin, e_pro, e_acc, e_mask, e_wg, e_work, e_fence, e_issue, e_pub);
     if (lane == 0) {
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every staged dZ piece is in HBM
 #pragma unroll

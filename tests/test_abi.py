@@ -72,7 +72,7 @@ def test_size_queries_are_host_functions_and_consistent():
     for t, width in ((bg, 256), (obj, 128)):
         blocks = (8 + 1) * (width // 64) + 128 // 64
         for M in (0, 1, 300):
-            want = M * blocks * 16384 + M * 8 * (width // 32) * 128 * 4
+            want = M * blocks * 16384 + M * (8 + 1) * (width // 32) * 128 * 4     # 8 trunk layers + the condition layer
             assert lib.durf_mlp_saved_bytes(C.byref(t), _lib.PREC_BF16, M, 128) == want
             # backward workspace = the dZ tile records, same shape as the saved activations
             assert lib.durf_mlp_workspace_bytes(C.byref(t), _lib.PREC_BF16, M, 128, 1) == M * blocks * 16384
