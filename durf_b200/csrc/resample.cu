@@ -154,7 +154,7 @@ resample128_kernel(const ResampleParams p) {
     if (k == 4 && lane != 0) break;                 // the 129th sample goes to lane 0
     float u;
     if (ur) u = fminf((float)i * p.s_step + ur[i] * p.s_jit, p.u_max);
-    else u = (i == S - 1) ? p.u_max : p.u_max * ((float)i / (float)(S - 1));
+    else u = (i == S - 1) ? p.u_max : p.u_max * ((float)i * 0.0078125f);      // i / 128: a power of two, the product is the exact quotient
     // last knot j in [0,127] with cdf[j] <= u (cdf[0] = 0 <= u, cdf[128] = 1 > u): branch-free bisection
     int j = 0;
 #pragma unroll

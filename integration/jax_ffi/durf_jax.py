@@ -1,49 +1,284 @@
-"""JAX side of the binding: registers the XLA-FFI handlers of libdurf_jax_ffi.so and exposes functions with the
-reference's `internal/mip.py` signatures, so `internal/obbpose_model.py` keeps its call sites.
+"""JAX side of the binding: registers the XLA-FFI handlers of libdurf_jax_ffi.so (integration/jax_ffi/durf_ffi.cc) and
+exposes differentiable functions with the argument meaning of the reference's call sites in
+`internal/obbpose_model.py` / `internal/mip.py`, so `MipNerfModel.__call__` keeps its structure and
+`jax.value_and_grad(loss_fn)` (train_boxpose.py:251) flows through the CUDA kernels:
 
-Needs a JAX new enough to have `jax.ffi` (>= 0.4.38) -- not installable in this repository's build image, so this module
-is documentation-grade source: it is exercised by nothing here and imports jax lazily.
+    forward handler                 backward handler        jax.custom_vjp below
+    DurfObbFrontendFwd              DurfObbFrontendBwd      obb_frontend        (d box_centers[ts])
+    DurfRaymarchFwd (fp32 / bf16)   DurfRaymarchBwd         encode_object_rays  (d origins_s, d dirs_s: the box-pose path)
+    DurfMlpFwd                      DurfMlpBwd              mlp                 (d params, d features)
+    DurfCompositeFwd                DurfCompositeBwd        volumetric_rendering_raw (d raw_rgb, d raw_density, d dirs_s)
+    DurfResampleFwd                 - (stop_gradient, mip.py:413-414)           resample_along_rays_t
+    DurfViewdirEnc, DurfCompactHits, DurfMlpPack            - (no differentiable inputs)
+
+Needs a JAX with `jax.ffi` (>= 0.4.38).  The build image of this repository has no jax, so nothing here is executed by its
+tests; `tests/test_ffi_shim.py` checks what can be checked without it: every handler named here is defined in durf_ffi.cc
+with the same operand / attribute / result counts, and durf_ffi.cc compiles against include/durf_b200.h.
+jax is imported lazily so that the module itself can be imported (and inspected) anywhere.
 """
 import ctypes
 import os
 
 _LIB = os.environ.get("DURF_JAX_FFI_LIB", os.path.join(os.path.dirname(__file__), "libdurf_jax_ffi.so"))
-RM_SAMPLE, RM_RANDOMIZED, RM_CONTRACT, RM_WEIGHTED = 1, 2, 4, 8
+_ABI = os.environ.get("DURF_ABI_LIB", os.path.join(os.path.dirname(__file__), "..", "..", "durf_b200", "libdurf_b200.so"))
+RM_SAMPLE, RM_RANDOMIZED, RM_CONTRACT, RM_WEIGHTED, RM_CYLINDER, RM_NO_INTEGRATE, RM_OUT_BF16_TILE = 1, 2, 4, 8, 16, 32, 64
+PREC_FP32, PREC_BF16 = 0, 1
+
+# handler -> (operands, attributes, results): the contract tests/test_ffi_shim.py checks against durf_ffi.cc
+HANDLERS = {
+    "DurfObbFrontendFwd": (4, 0, 7),
+    "DurfObbFrontendBwd": (7, 2, 1),
+    "DurfCompactHits": (1, 1, 2),
+    "DurfRaymarchFwd": (10, 5, 2),
+    "DurfRaymarchBwd": (9, 5, 2),
+    "DurfViewdirEnc": (1, 1, 1),
+    "DurfMlpPack": (1, 6, 1),
+    "DurfMlpFwd": (8, 10, 4),
+    "DurfMlpBwd": (10, 9, 3),
+    "DurfCompositeFwd": (4, 3, 6),
+    "DurfCompositeBwd": (8, 3, 3),
+    "DurfResampleFwd": (3, 2, 1),
+}
 
 
 def register():
     import jax
     lib = ctypes.CDLL(_LIB)
-    for name in ("DurfRaymarchFwd", "DurfCompositeFwd", "DurfResampleFwd", "DurfMlpFwd"):
+    for name in HANDLERS:
         jax.ffi.register_ffi_target(name, jax.ffi.pycapsule(getattr(lib, name)), platform="CUDA")
 
 
-def sample_and_encode(t_rand, origins, directions, radii, num_samples, near, far, randomized, contract, min_deg, max_deg):
-    """mip.sample_along_rays -> [mip360.new_space] -> mip.integrated_pos_enc in one custom call:
-    returns (t_vals[B,N+1], features[B,N,6*(max_deg-min_deg)]).  `t_rand` replaces the PRNG key (explicit U[0,1) draws)."""
+class _Abi:
+    """Host-side size queries of the C ABI (pure arithmetic, callable at trace time)."""
+    _lib = None
+
+    class Topology(ctypes.Structure):
+        _fields_ = [(n, ctypes.c_int32) for n in ("in_dim", "width", "depth", "skip", "cond_dim", "cond_width")]
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            cls._lib = ctypes.CDLL(_ABI)
+            for f in ("durf_mlp_workspace_bytes", "durf_mlp_saved_bytes"):
+                getattr(cls._lib, f).restype = ctypes.c_size_t
+            cls._lib.durf_mlp_packed_bytes.restype = ctypes.c_int64
+        return cls._lib
+
+
+def _sizes(topo, precision, M, N, training):
+    t = _Abi.Topology(*topo)
+    lib = _Abi.lib()
+    ws = int(lib.durf_mlp_workspace_bytes(ctypes.byref(t), precision, M, N, int(training)))
+    saved = int(lib.durf_mlp_saved_bytes(ctypes.byref(t), precision, M, N)) if training else 0
+    return max(ws, 16), saved
+
+
+def _topo_attrs(topo):
+    return dict(zip(("in_dim", "width", "depth", "skip", "cond_dim", "cond_width"), (int(x) for x in topo)))
+
+
+# ---- K0 ------------------------------------------------------------------------------------------------------------
+def obb_frontend(origins, directions, box, ext, pose_grad=True, rot_grad=True):
+    """world2object_rpy + ray_box_intersection + the scene-graph merge (obbpose_model.py:99-131) for box = box_centers[ts]
+    [K,6]: returns (origins_s, dirs_s, hit[B,K] int32, zi, zo, zo_ret, nhit); differentiable w.r.t. `box` through origins_s / dirs_s."""
     import jax
     import jax.numpy as jnp
+    B, K = origins.shape[0], box.shape[0]
+    f = jnp.float32
+    outs = (jax.ShapeDtypeStruct((B, 3), f), jax.ShapeDtypeStruct((B, 3), f), jax.ShapeDtypeStruct((B, K), jnp.int32),
+            jax.ShapeDtypeStruct((B, K), f), jax.ShapeDtypeStruct((B, K), f), jax.ShapeDtypeStruct((B,), f),
+            jax.ShapeDtypeStruct((B,), f))
+
+    @jax.custom_vjp
+    def fe(box_):
+        return jax.ffi.ffi_call("DurfObbFrontendFwd", outs)(origins, directions, box_, ext)
+
+    def fe_fwd(box_):
+        res = fe(box_)
+        return res, (box_, res[2])
+
+    def fe_bwd(saved, cts):
+        box_, hit = saved
+        d_os, d_ds = cts[0], cts[1]
+        d_box = jax.ffi.ffi_call("DurfObbFrontendBwd", jax.ShapeDtypeStruct((K, 6), f), input_output_aliases={6: 0})(
+            origins, directions, box_, hit, d_os, d_ds, jnp.zeros((K, 6), f), pose_grad=int(pose_grad), rot_grad=int(rot_grad))
+        return (d_box,)
+
+    fe.defvjp(fe_fwd, fe_bwd)
+    return fe(box)
+
+
+def compact_hits(hit, k):
+    """Indices of the rays that hit object k (unordered) and their count [1] (obbpose_model.py:174-201 evaluates every ray
+    and masks; evaluating the hit rays only is result-identical)."""
+    import jax
+    import jax.numpy as jnp
+    B = hit.shape[0]
+    return jax.ffi.ffi_call("DurfCompactHits", (jax.ShapeDtypeStruct((B,), jnp.int32), jax.ShapeDtypeStruct((1,), jnp.int32)))(hit, k=int(k))
+
+
+# ---- K1 ------------------------------------------------------------------------------------------------------------
+def _raymarch(origins, dirs, radii, near, far, t_rand, ray_mult, t_vals, ray_index, count, rows, num_samples, min_deg, max_deg, flags,
+              alpha):
+    import jax
+    import jax.numpy as jnp
+    F = 6 * (max_deg - min_deg) + (3 if flags & RM_WEIGHTED else 0)
+    feat = (jax.ShapeDtypeStruct((rows, 128 * 64), jnp.bfloat16) if flags & RM_OUT_BF16_TILE
+            else jax.ShapeDtypeStruct((rows, num_samples, F), jnp.float32))
+    outs = (jax.ShapeDtypeStruct((origins.shape[0], num_samples + 1), jnp.float32), feat)
+    return jax.ffi.ffi_call("DurfRaymarchFwd", outs, input_output_aliases={7: 0})(
+        origins, dirs, radii.reshape(-1), near, far, t_rand, ray_mult, t_vals, ray_index, count, num_samples=int(num_samples),
+        min_deg=int(min_deg), max_deg=int(max_deg), flags=int(flags), alpha=float(alpha))
+
+
+def sample_and_encode(t_rand, origins, directions, radii, num_samples, near, far, randomized, contract, min_deg, max_deg,
+                      ray_mult=None, bf16_tiles=False):
+    """mip.sample_along_rays -> [mip360.new_space] -> mip.integrated_pos_enc in one custom call (level 0 of the background):
+    returns (t_vals[B,N+1], features).  `t_rand` replaces the PRNG key (explicit U[0,1) draws).  No differentiable input."""
+    import jax.numpy as jnp
     B = origins.shape[0]
-    flags = RM_SAMPLE | (RM_RANDOMIZED if randomized else 0) | (RM_CONTRACT if contract else 0)
-    out = (jax.ShapeDtypeStruct((B, num_samples + 1), jnp.float32),
-           jax.ShapeDtypeStruct((B, num_samples, 6 * (max_deg - min_deg)), jnp.float32))
-    empty = jnp.zeros((0,), jnp.float32)
-    return jax.ffi.ffi_call("DurfRaymarchFwd", out)(origins, directions, radii.reshape(-1), near.reshape(-1), far.reshape(-1),
-                                                    t_rand, empty, num_samples=num_samples, min_deg=min_deg, max_deg=max_deg,
-                                                    flags=flags, alpha=0.0)
+    e = jnp.zeros((0,), jnp.float32)
+    ei = jnp.zeros((0,), jnp.int32)
+    flags = RM_SAMPLE | (RM_RANDOMIZED if randomized else 0) | (RM_CONTRACT if contract else 0) | (RM_OUT_BF16_TILE if bf16_tiles else 0)
+    return _raymarch(origins, directions, radii, near.reshape(-1), far.reshape(-1), t_rand if randomized else e,
+                     e if ray_mult is None else ray_mult, jnp.zeros((B, num_samples + 1), jnp.float32), ei, ei, B, num_samples,
+                     min_deg, max_deg, flags, 0.0)
 
 
+def encode(t_vals, origins, directions, radii, contract, min_deg, max_deg, ray_mult=None, bf16_tiles=False):
+    """cast_rays -> [new_space] -> integrated_pos_enc on given (resampled, stop_gradient'ed) fenceposts."""
+    import jax.numpy as jnp
+    B, S = t_vals.shape
+    e = jnp.zeros((0,), jnp.float32)
+    ei = jnp.zeros((0,), jnp.int32)
+    flags = (RM_CONTRACT if contract else 0) | (RM_OUT_BF16_TILE if bf16_tiles else 0)
+    return _raymarch(origins, directions, radii, e, e, e, e if ray_mult is None else ray_mult, t_vals, ei, ei, B, S - 1, min_deg,
+                     max_deg, flags, 0.0)[1]
+
+
+def encode_object_rays(t_vals, origins_s, dirs_s, radii, ray_index, count, rows, alpha, min_deg, max_deg):
+    """mip.weighted_ipe (BARF coarse-to-fine weights, mip.py:182-223) of the rays in `ray_index`, fp32 [rows, N, 63];
+    differentiable w.r.t. origins_s / dirs_s (the gradient path into the SE(3) box parameters)."""
+    import jax
+    import jax.numpy as jnp
+    B, S = t_vals.shape
+    N = S - 1
+    e = jnp.zeros((0,), jnp.float32)
+    attrs = dict(num_samples=N, min_deg=int(min_deg), max_deg=int(max_deg), flags=RM_WEIGHTED, alpha=float(alpha))
+
+    @jax.custom_vjp
+    def enc(o, d):
+        return _raymarch(o, d, radii, e, e, e, e, t_vals, ray_index, count, rows, N, min_deg, max_deg, RM_WEIGHTED, alpha)[1]
+
+    def enc_fwd(o, d):
+        return enc(o, d), (o, d)
+
+    def enc_bwd(saved, d_feat):
+        o, d = saved
+        f = jnp.float32
+        outs = (jax.ShapeDtypeStruct((B, 3), f), jax.ShapeDtypeStruct((B, 3), f))
+        return jax.ffi.ffi_call("DurfRaymarchBwd", outs, input_output_aliases={7: 0, 8: 1})(
+            o, d, radii.reshape(-1), t_vals, ray_index, count, d_feat, jnp.zeros((B, 3), f), jnp.zeros((B, 3), f), **attrs)
+
+    enc.defvjp(enc_fwd, enc_bwd)
+    return enc(origins_s, dirs_s)
+
+
+def pos_enc_viewdirs(viewdirs, deg):
+    """mip.pos_enc(viewdirs, 0, deg, append_identity=True) (mip.py:36-45)."""
+    import jax
+    import jax.numpy as jnp
+    return jax.ffi.ffi_call("DurfViewdirEnc", jax.ShapeDtypeStruct((viewdirs.shape[0], 3 + 6 * deg), jnp.float32))(viewdirs, deg=int(deg))
+
+
+# ---- K2 ------------------------------------------------------------------------------------------------------------
+def mlp_pack(params, topo):
+    """fp32 parameter blob (flax creation order Dense_0.., kernel then bias) -> tensor-core weight image; after every update."""
+    import jax
+    import jax.numpy as jnp
+    t = _Abi.Topology(*topo)
+    n = int(_Abi.lib().durf_mlp_packed_bytes(ctypes.byref(t)))
+    return jax.ffi.ffi_call("DurfMlpPack", jax.ShapeDtypeStruct((n,), jnp.uint8))(params, **_topo_attrs(topo))
+
+
+def mlp(params, features, cond, topo, num_rays, num_samples=128, precision=PREC_BF16, packed=None, ray_index=None, count=None,
+        into=None, want_d_features=False):
+    """MLP.__call__ / BoxMLP.__call__ (obbpose_model.py:294-354, 358-418): returns (raw_rgb[B,N,3], raw_density[B,N]).
+    `into` = (raw_rgb, raw_density) of the background: an object network ADDS its hit rows (obbpose_model.py:203-204).
+    Differentiable w.r.t. `params` (flat blob) and, with want_d_features (fp32 features; the box-pose path), `features`."""
+    import jax
+    import jax.numpy as jnp
+    f = jnp.float32
+    B = cond.shape[0]
+    ei = jnp.zeros((0,), jnp.int32)
+    ray_index = ei if ray_index is None else ray_index
+    count = ei if count is None else count
+    packed_ = jnp.zeros((0,), jnp.uint8) if packed is None else packed
+    acc = into is not None
+    rgb0, den0 = into if acc else (jnp.zeros((B, num_samples, 3), f), jnp.zeros((B, num_samples), f))
+    attrs = dict(_topo_attrs(topo), precision=int(precision), num_rays=int(num_rays), num_samples=int(num_samples))
+    ws_fwd, saved_bytes = _sizes(topo, precision, num_rays, num_samples, True)
+    ws_bwd, _ = _sizes(topo, precision, num_rays, num_samples, True)
+    n_params = params.shape[0]
+
+    def call_fwd(p, x, training):
+        outs = (jax.ShapeDtypeStruct(rgb0.shape, f), jax.ShapeDtypeStruct(den0.shape, f),
+                jax.ShapeDtypeStruct((saved_bytes if training else 0,), jnp.uint8), jax.ShapeDtypeStruct((ws_fwd,), jnp.uint8))
+        return jax.ffi.ffi_call("DurfMlpFwd", outs, input_output_aliases={6: 0, 7: 1})(
+            x, cond, p, packed_, ray_index, count, rgb0, den0, accumulate=int(acc), **attrs)
+
+    @jax.custom_vjp
+    def run(p, x):
+        r = call_fwd(p, x, False)
+        return r[0], r[1]
+
+    def run_fwd(p, x):
+        r = call_fwd(p, x, True)
+        return (r[0], r[1]), (p, x, r[2])
+
+    def run_bwd(res, cts):
+        p, x, saved = res
+        d_rgb, d_den = cts
+        n_dx = num_rays * num_samples if want_d_features else 0
+        outs = (jax.ShapeDtypeStruct((n_params,), f), jax.ShapeDtypeStruct((n_dx, topo[0]) if n_dx else (0,), f),
+                jax.ShapeDtypeStruct((ws_bwd,), jnp.uint8))
+        d_p, d_x, _ = jax.ffi.ffi_call("DurfMlpBwd", outs, input_output_aliases={9: 0})(
+            x, cond, p, packed_, ray_index, count, saved, d_rgb, d_den, jnp.zeros((n_params,), f), **attrs)
+        return d_p, (d_x.reshape(x.shape) if want_d_features else jnp.zeros_like(x))
+
+    run.defvjp(run_fwd, run_bwd)
+    return run(params, features)
+
+
+# ---- K3 / K4 ---------------------------------------------------------------------------------------------------------
 def volumetric_rendering_raw(raw_rgb, raw_density, t_vals, dirs, white_bkgd, rand_bkgd, density_bias=-1.0):
-    """obbpose_model.py:243-245 + mip.volumetric_rendering (mip.py:285-327) -> the reference's 7-tuple."""
+    """obbpose_model.py:243-245 + mip.volumetric_rendering (mip.py:285-327) -> the reference's 7-tuple; differentiable w.r.t.
+    raw_rgb, raw_density and dirs (t_vals carry no gradient: mip.py:413-414)."""
     import jax
     import jax.numpy as jnp
     B, N = raw_density.shape[:2]
     f = jnp.float32
-    out = (jax.ShapeDtypeStruct((B, 3), f), jax.ShapeDtypeStruct((B,), f), jax.ShapeDtypeStruct((B,), f),
-           jax.ShapeDtypeStruct((B, N), f), jax.ShapeDtypeStruct((B, N), f), jax.ShapeDtypeStruct((B, N), f))
-    comp_rgb, depth, acc, weights, t_mids, t_dists = jax.ffi.ffi_call("DurfCompositeFwd", out)(
-        raw_rgb, raw_density.reshape(B, N), t_vals, dirs, white_bkgd=int(white_bkgd), rand_bkgd=int(rand_bkgd),
-        density_bias=float(density_bias))
+    attrs = dict(white_bkgd=int(white_bkgd), rand_bkgd=int(rand_bkgd), density_bias=float(density_bias))
+    outs = (jax.ShapeDtypeStruct((B, 3), f), jax.ShapeDtypeStruct((B,), f), jax.ShapeDtypeStruct((B,), f),
+            jax.ShapeDtypeStruct((B, N), f), jax.ShapeDtypeStruct((B, N), f), jax.ShapeDtypeStruct((B, N), f))
+
+    @jax.custom_vjp
+    def comp(rgb, den, d):
+        return jax.ffi.ffi_call("DurfCompositeFwd", outs)(rgb, den.reshape(B, N), t_vals, d, **attrs)
+
+    def comp_fwd(rgb, den, d):
+        return comp(rgb, den, d), (rgb, den, d)
+
+    def comp_bwd(saved, cts):
+        rgb, den, d = saved
+        g_rgb, g_depth, g_acc, g_w = cts[0], cts[1], cts[2], cts[3]      # t_mids / t_dists depend on t_vals only
+        bouts = (jax.ShapeDtypeStruct((B, N, 3), f), jax.ShapeDtypeStruct((B, N), f), jax.ShapeDtypeStruct((B, 3), f))
+        d_rgb, d_den, d_dirs = jax.ffi.ffi_call("DurfCompositeBwd", bouts)(rgb, den.reshape(B, N), t_vals, d, g_rgb, g_depth, g_acc,
+                                                                            g_w, **attrs)
+        return d_rgb, d_den.reshape(den.shape), d_dirs
+
+    comp.defvjp(comp_fwd, comp_bwd)
+    comp_rgb, depth, acc, weights, t_mids, t_dists = comp(raw_rgb, raw_density, dirs)
     return comp_rgb, depth, acc, weights, t_vals, t_mids, t_dists
 
 
@@ -53,8 +288,5 @@ def resample_along_rays_t(u_rand, t_vals, weights, randomized, resample_padding)
     import jax.numpy as jnp
     u = u_rand if randomized else jnp.zeros((0,), jnp.float32)
     new_t = jax.ffi.ffi_call("DurfResampleFwd", jax.ShapeDtypeStruct(t_vals.shape, jnp.float32))(
-        t_vals, weights, u, resample_padding=float(resample_padding), blurpool=1)
+        t_vals, jax.lax.stop_gradient(weights), u, resample_padding=float(resample_padding), blurpool=1)
     return jax.lax.stop_gradient(new_t)
-
-# Gradients: wrap each forward in jax.custom_vjp whose backward rule calls the matching *_bwd entry point
-# (durf_composite_bwd, durf_mlp_bwd, durf_raymarch_bwd, durf_obb_frontend_bwd) through the same ffi_call mechanism.
