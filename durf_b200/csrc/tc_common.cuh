@@ -127,8 +127,12 @@ __device__ __forceinline__ void umma_kblock_conv(uint32_t d_tmem, uint32_t a, ui
         ".reg .b32 bl, al, cnt;\n"
         ".reg .b16 mk;\n"
         "cvt.u16.u32 mk, %16;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 qa, [%6], %7;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 qb, [%9], %10;\n"
+        // a probe goes through the memory pipe of the issuing thread: only the barriers the next step really needs are probed
+        // (need_x is a compile-time constant at most call sites, so the unused probe disappears altogether)
+        "setp.ne.u32 t, %8, 0;\n setp.ne.u32 u, %11, 0;\n"
+        "setp.ne.u32 qa, %8, %8;\n setp.ne.u32 qb, %8, %8;\n"
+        "@t mbarrier.test_wait.parity.shared::cta.b64 qa, [%6], %7;\n"
+        "@u mbarrier.test_wait.parity.shared::cta.b64 qb, [%9], %10;\n"
         "elect.sync _|e, 0xffffffff;\n"
         "setp.ne.b32 pacc, %5, 0;\n"
         "setp.eq.u32 ptrue, %5, %5;\n"
@@ -159,8 +163,12 @@ __device__ __forceinline__ void umma_kblock_conv(uint32_t d_tmem, uint32_t a, ui
         ".reg .b32 bl, al, cnt;\n"
         ".reg .b16 mk;\n"
         "cvt.u16.u32 mk, %16;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 qa, [%6], %7;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 qb, [%9], %10;\n"
+        // a probe goes through the memory pipe of the issuing thread: only the barriers the next step really needs are probed
+        // (need_x is a compile-time constant at most call sites, so the unused probe disappears altogether)
+        "setp.ne.u32 t, %8, 0;\n setp.ne.u32 u, %11, 0;\n"
+        "setp.ne.u32 qa, %8, %8;\n setp.ne.u32 qb, %8, %8;\n"
+        "@t mbarrier.test_wait.parity.shared::cta.b64 qa, [%6], %7;\n"
+        "@u mbarrier.test_wait.parity.shared::cta.b64 qb, [%9], %10;\n"
         "elect.sync _|e, 0xffffffff;\n"
         "setp.ne.b32 pacc, %5, 0;\n"
         "setp.eq.u32 ptrue, %5, %5;\n"
