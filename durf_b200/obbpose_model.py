@@ -263,16 +263,19 @@ class MipNerfModel:
             raw_grads.append((g_rgb, g_den))
             if pose_opt:
                 d_ds += g_dirs * (fe['nhit'] > 0).float()[:, None]            # only object rays carry pose-dependent dirs
-            if overlap is not None:
-                overlap(bt, lvl['feat_bg'], viewenc, variables.blob('MLP_0'), lvl['saved_bg'], g_rgb, g_den,
-                        variables.blob_of(d_flat, 'MLP_0'), M=B, N=N, packed=variables.packed.get('MLP_0'))
-            else:
-                ops.mlp_bwd(bt, lvl['feat_bg'], viewenc, variables.blob('MLP_0'), lvl['saved_bg'], g_rgb, g_den,
-                            variables.blob_of(d_flat, 'MLP_0'), M=B, N=N, precision=prec, packed=variables.packed.get('MLP_0'))
-        if overlap is not None:
-            overlap.join()
-        done('MLP_0')
-        for k in range(K if self.dynamics else 0):
+        # The networks' backward passes are independent of each other (disjoint slices of d_flat, read-only upstream gradients):
+        # without pose optimisation every object network runs on its own side stream next to the background network.  That
+        # matters for small batches, where each of the ~12 backward kernels is a few waves long and latency-bound (the
+        # reference's shipped batch is 512 rays); large batches fill the GPU with the background network alone.
+        n_obj = K if self.dynamics else 0
+        side = _object_streams(d_flat.device, n_obj) if (n_obj and not pose_opt and ctx['obj_prec'] == L.PREC_BF16 and
+                                                        os.environ.get('DURF_OBJ_STREAMS', '1') != '0') else None
+        cur = torch.cuda.current_stream()
+        if side is not None:
+            for sk in side:
+                sk.wait_stream(cur)
+
+        def object_backward(k):
             for lvl, (g_rgb, g_den) in zip(ctx['levels'], raw_grads):
                 o = lvl['obj'][k]
                 if o is None:
@@ -288,8 +291,28 @@ class MipNerfModel:
                     ops.raymarch_bwd(fe['origins_s'], fe['dirs_s'], ctx['radii'], lvl['t_vals'], dfeat, weighted=True,
                                      alpha=ctx['alpha'], min_deg=self.min_deg_point, max_deg=self.max_deg_point, ray_index=idx,
                                      rows=o['rows'], count=o.get('count'), d_origins=go, d_dirs=gd)
-                    d_os += go
-                    d_ds += gd
+                    d_os.add_(go)
+                    d_ds.add_(gd)
+
+        if side is not None:
+            for k, sk in enumerate(side):
+                with torch.cuda.stream(sk):
+                    object_backward(k)
+        for lvl, (g_rgb, g_den) in zip(ctx['levels'], raw_grads):
+            if overlap is not None:
+                overlap(bt, lvl['feat_bg'], viewenc, variables.blob('MLP_0'), lvl['saved_bg'], g_rgb, g_den,
+                        variables.blob_of(d_flat, 'MLP_0'), M=B, N=N, packed=variables.packed.get('MLP_0'))
+            else:
+                ops.mlp_bwd(bt, lvl['feat_bg'], viewenc, variables.blob('MLP_0'), lvl['saved_bg'], g_rgb, g_den,
+                            variables.blob_of(d_flat, 'MLP_0'), M=B, N=N, precision=prec, packed=variables.packed.get('MLP_0'))
+        if overlap is not None:
+            overlap.join()
+        done('MLP_0')
+        for k in range(n_obj):
+            if side is not None:
+                cur.wait_stream(side[k])
+            else:
+                object_backward(k)
             done(f'BoxMLP_{k}')
         for k in range(0 if self.dynamics else K):
             done(f'BoxMLP_{k}')                                              # static scene: object networks get no gradient
@@ -303,6 +326,17 @@ class MipNerfModel:
             else:
                 bc[ctx['ts']] += d_box
         done('box_centers')
+
+
+_OBJ_STREAMS: Dict[Any, List[torch.cuda.Stream]] = {}
+
+
+def _object_streams(device, n: int) -> List[torch.cuda.Stream]:
+    """One side stream per object network (created once per device)."""
+    pool = _OBJ_STREAMS.setdefault(device, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
 
 
 def _rand_buffers(rng, randomized: bool, B: int, N: int, levels: int, density_noise: float, dev) -> dict:
