@@ -5,9 +5,10 @@
 It reads the reference's .gin files unchanged (`utils.load_gin`), builds the model (`construct_mipnerf`), restores the
 newest checkpoint (`init_step = state.step + 1`, :404-406), runs the schedules of :347-367 (log-lerp learning rate with
 sine warm-up, eps, BARF alpha), the train step, the rays/sec logging of :518-528, periodic checkpoints (:529-532) and a
-final test render.  No dataset ships with the reference (its loaders are out of scope): batches come
-from `SyntheticTimestepDataset`, which reproduces the loaders' batch contract ('timestep' batching: all rays of a batch
-share one `ts`; fields rays/pixels/depth/sky/ext/init/ts) on synthetic pinhole rays."""
+final test render.  With `--data_dir` batches come from the CARLA loader (`durf_b200.obbpose_dataset.Carla`, the mirror of
+internal/obbpose_dataset.py's `Carla`); no dataset ships with the reference, so by default they come from
+`SyntheticTimestepDataset`, which reproduces the loader's batch contract ('timestep' batching: all rays of a batch share one
+`ts`; fields rays/pixels/depth/sky/ext/init/ts) on synthetic pinhole rays."""
 from __future__ import annotations
 
 import argparse
@@ -18,7 +19,7 @@ from typing import Dict, Iterator
 import numpy as np
 import torch
 
-from . import checkpoint, math as dmath, parallel, synthetic as S
+from . import checkpoint, math as dmath, obbpose_dataset, parallel, synthetic as S
 from .obbpose_model import MipNerfModel, Variables, render_camera
 from .train import TrainState, train_step
 from .utils import Config, Rays, load_gin
@@ -52,17 +53,39 @@ class SyntheticTimestepDataset:
                        ext=to(self.ext), ts=ts, init=self.centers)
 
 
+class DiskDataset:
+    """The CARLA loader's numpy batches (durf_b200.obbpose_dataset.Carla) as device batches: pinned staging, non-blocking
+    copies on the current stream (what utils.shard / device_put does in the reference, train_boxpose.py:424)."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, device
+
+    def _to_dev(self, b):
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).pin_memory().to(self.device, non_blocking=True)
+        return dict(rays=Rays(*[up(r) for r in b['rays']]), pixels=up(b['pixels']), depth=up(b['depth']), sky=up(b['sky']),
+                    ext=up(b['ext']), init=np.asarray(b['init'], np.float32), ts=int(b['ts']))
+
+    def peek(self):
+        return self._to_dev(self.loader.peek())
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        return self._to_dev(next(self.loader))
+
+
 def main(argv=None) -> Dict:
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("--gin_file", required=True)
     ap.add_argument("--train_dir", required=True)
-    ap.add_argument("--data_dir", default=None, help="accepted for CLI parity; batches are synthetic")
     ap.add_argument("--max_steps", type=int, default=None)
     ap.add_argument("--batch_size", type=int, default=None)
     ap.add_argument("--save_every", type=int, default=50000)
     ap.add_argument("--print_every", type=int, default=100)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--render_rows", type=int, default=0, help="rows of the final 1920-wide test render (0: none)")
+    ap.add_argument("--data_dir", default=None, help="an on-disk CARLA scene (internal/obbpose_dataset.py layout); default: synthetic batches")
     args = ap.parse_args(argv)
 
     rank, world, local = parallel.env_rank_world()
@@ -78,7 +101,10 @@ def main(argv=None) -> Dict:
     config = Config(**cfg_kw)
     model = MipNerfModel(precision=args.precision, timesteps=config.timesteps,
                          **{k: v for k, v in model_kw.items() if k in MipNerfModel.__dataclass_fields__})
-    dataset = SyntheticTimestepDataset(config, model.num_objects, dev, seed=S.SEED, rank=rank)
+    if args.data_dir:
+        dataset = DiskDataset(obbpose_dataset.get_dataset('train', args.data_dir, config), dev)      # train_boxpose.py:331
+    else:
+        dataset = SyntheticTimestepDataset(config, model.num_objects, dev, seed=S.SEED, rank=rank)
     variables = model.init(np.random.default_rng(20200823), dataset.peek()["init"], device=dev)       # train_boxpose.py:325
     state = checkpoint.restore_checkpoint(args.train_dir, TrainState.create(variables))
     if world > 1:
@@ -116,8 +142,15 @@ def main(argv=None) -> Dict:
     out = dict(last=last, losses=losses, step=state.step)
     if args.render_rows > 0 and rank == 0:
         fn = lambda rng, b: model.apply(variables, rng, b["rays"], None, b["ext"], b["ts"], False, False, False, b["alpha"])
-        rgb, dist, acc = render_camera(fn, dataset.c2w[0], S.WAYMO_W, args.render_rows, S.FOCAL, config.near, config.far, None,
-                                       torch.from_numpy(dataset.ext).to(dev), 0, None, alpha_fn(state.step))
+        if args.data_dir:      # the first held-out frame of the scene, rays generated on the device
+            test = obbpose_dataset.get_dataset('test', args.data_dir, config)
+            tb, cam = test.peek(), test.camera(0)
+            rgb, dist, acc = render_camera(fn, cam['c2w'], cam['width'], min(args.render_rows, cam['height']), cam['focal'], cam['near'],
+                                           cam['far'], None, torch.from_numpy(np.asarray(tb['ext'], np.float32)).to(dev), int(tb['ts']),
+                                           None, alpha_fn(state.step))
+        else:
+            rgb, dist, acc = render_camera(fn, dataset.c2w[0], S.WAYMO_W, args.render_rows, S.FOCAL, config.near, config.far, None,
+                                           torch.from_numpy(dataset.ext).to(dev), 0, None, alpha_fn(state.step))
         out["render_mean_rgb"] = float(rgb.mean())
     return out
 

@@ -50,6 +50,18 @@ class Config:
     randomized: bool = True
     white_bkgd: bool = False
     rand_bkgd: bool = False
+    # dataset loader (internal/utils.py:93-104, values of configs/carla_dyn.gin)
+    dataset_loader: str = 'carla_dyn'
+    batching: str = 'timestep'
+    factor: int = 4
+    spherify: bool = True
+    centering: bool = True
+    random_box: bool = False
+    random_yaw: bool = False
+    box_noise: float = 0.5
+    yaw_noise: float = 5.0
+    render_path: bool = False
+    llffhold: int = 11
 
 
 def load_gin(path: str):

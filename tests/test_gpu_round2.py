@@ -218,6 +218,35 @@ def test_overlapped_backward_equals_the_serial_backward(B, monkeypatch):
     assert rel_g <= max(1e-5, 3.0 * noise), f"graph-captured overlapped backward: {rel_g:.3e}"
 
 
+@pytest.mark.parametrize("randomized", [False, True])
+def test_fused_raymarch_is_the_separate_raymarch(randomized):
+    """with `fuse_raymarch` the tcgen05 MLP kernel generates its own input tiles (mip.py:155-282, mip360.py:47-79
+    inside K2) - the same device functions as the stand-alone ray-march kernel, so the whole model output must be IDENTICAL,
+    bit for bit, to the path with separate durf_raymarch_fwd launches: background (contraction, ray multiplier) and object
+    networks (weighted IPE on compacted hit rays), sampled and resampled levels, inference and the training forward (where
+    the generated tile is also stored for the weight-gradient kernel)."""
+    sc = H.scene(B=700, K=2, seed=41)
+    outs = {}
+    for fuse in (True, False):
+        model = _model(precision='bf16', fuse_raymarch=fuse)
+        v = H.cuda_variables(sc, model)
+        rng = dict(t_rand=cu(sc['t_rand']), u_rand=cu(sc['u_rand'])) if randomized else None
+        for training in (False, True):
+            ctx = {} if training else None
+            ret = model.apply(v, rng, H.cuda_rays(sc), None, cu(sc['ext']), torch.tensor([1]), randomized, False, False, 4.5, ctx=ctx)
+            torch.cuda.synchronize()
+            outs[(fuse, training)] = [(lv[0].clone(), lv[1].clone(), lv[2].clone(), lv[3].clone(), lv[4].clone()) for lv in ret]
+            if training:
+                outs[(fuse, 'feat')] = [lvl['feat_bg'].clone() for lvl in ctx['levels']]
+    for training in (False, True):
+        for a, b in zip(outs[(True, training)], outs[(False, training)]):
+            for x, y, name in zip(a, b, ('comp_rgb', 'depth', 'acc', 'weights', 't_vals')):
+                assert torch.equal(x, y), f"{name} differs between the fused and the separate ray-march (training={training}): " \
+                                          f"max |d| = {float((x - y).abs().max()):.3e}"
+    for x, y in zip(outs[(True, 'feat')], outs[(False, 'feat')]):
+        assert torch.equal(x.view(torch.int16), y.view(torch.int16)), "stored feature tiles differ"
+
+
 def test_loss_value_is_bit_reproducible_and_step_has_no_host_sync():
     """The loss reduction is deterministic (fixed-order block partials instead of float atomics), and a bf16 train step issues
     no device->host read (checked with torch's sync debug mode)."""
