@@ -626,8 +626,8 @@ def main():
                 dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
                 config=dict(workload=WORKLOAD_C2, rays_per_step_per_gpu=n_rays, chunk=chunk, mlp="8x256 + cond 128, random init",
                             sharding="one camera frame per GPU, no collective",
-                            l2="every chunk streams 65,536 new rays (3 MB of rays + 34 MB of t_vals + 134 MB of raw outputs + 34 MB of "
-                               "view bias per level > the 126 MB L2 over a frame of 38 chunks); no explicit flush"),
+                            l2="every chunk streams 65,536 new rays (3 MB of rays + 34 MB of t_vals + 134 MB of raw outputs per level "
+                               "> the 126 MB L2 over a frame of 38 chunks); no explicit flush"),
                 clocks=dict(sm_mhz=clocks["sm_mhz"], sm_max_mhz=clocks["sm_max_mhz"], reasons=clocks["reasons"],
                             samples=clocks["samples"], power_w_max=clocks.get("power_w_max")),
                 e2e=dict(value=e2e_v, unit="rays/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e,

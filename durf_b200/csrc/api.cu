@@ -80,7 +80,8 @@ extern "C" size_t durf_mlp_workspace_bytes(const DurfMlpTopology* topo, int32_t 
   const int64_t R = (int64_t)M * N;
   if (precision == DURF_PREC_FP32)
     return sizeof(float) * (training ? mlp_fp32_bwd_floats(*topo, R) : mlp_fp32_infer_floats(*topo, R));
-  // inference / forward: per-tile view bias of the condition layer; backward: the dz tile records read by wgrad
+  // forward: nothing (the per-tile view bias of the condition layer is formed inside the kernel); backward: the dz tile
+  // records read by wgrad
   if (training) return mlp_tc_bwd_supported(*topo) ? (size_t)M * mlp_tc_saved_blocks(*topo) * 16384 : 0;
   return mlp_tc_workspace_bytes(*topo, M);
 }

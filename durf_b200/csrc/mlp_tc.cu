@@ -74,7 +74,7 @@ struct StageUse {
 struct TcParams {
   const uint8_t* feat;       // bf16 tile images, 16 KB per tile
   const float* cond;         // [B, cond_dim]
-  const float* vbias;        // [M, 128] per-tile bias of the condition layer (b + W_view^T enc), from cond_bias_kernel
+  int off_bcond;             // bias of the condition layer inside the parameter blob (its view part is added per tile, see view_bias)
   const float* params;       // fp32 blob
   const uint8_t* packed;     // weight image
   const int32_t* ray_index;
@@ -209,8 +209,8 @@ struct TcCfg {
   static constexpr int OFF_BIAS = OFF_STG + STG_BYTES;                // fp32 [MAX_BIAS_LAYERS][W]
   static constexpr int OFF_WDEN = OFF_BIAS + MAX_BIAS_LAYERS * W * 4; // fp32 [W]
   static constexpr int OFF_WRGB = OFF_WDEN + W * 4;                   // fp32 [3][128]
-  static constexpr int OFF_VBIAS = OFF_WRGB + 3 * 128 * 4;            // fp32 [128]
-  static constexpr int OFF_PART = OFF_VBIAS + 128 * 4;                // fp32 [4][128] partial density / rgb of the upper column warps
+  static constexpr int OFF_VBIAS = OFF_WRGB + 3 * 128 * 4;            // fp32 [128] this tile's | [2][128] the coming tiles' view bias
+  static constexpr int OFF_PART = OFF_VBIAS + 3 * 128 * 4;            // fp32 [4][128] partial density / rgb of the upper column warps
   static constexpr int OFF_MISC = OFF_PART + 4 * 128 * 4;             // head biases [4] + tmem ptr + barriers
   static constexpr int MISC_BYTES = 512;
   static constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;     // + alignment slack
@@ -265,6 +265,23 @@ __device__ __forceinline__ void issue_layer(IssueState& st, uint32_t sbase, uint
                               bar_acc_full(LS.nh[i]), LS.commit[i] ? 1u : 0u, bar_empty(st.stage), stage_last ? 1u : 0u, rel_mask);
     if (stage_last) { st.stage = next_stage; st.phase = next_phase; }
   }
+}
+
+// Per-tile bias of the condition layer: vb[j] = b_cond[j] + sum_i enc(viewdir of the tile's ray)[i] * W_cond[width + i][j]
+// (obbpose_model.py:343-350).  The view direction is constant along a ray, so these 27 input columns never occupy
+// tensor-core K; the 64 threads of warps 2-3 form the row for the NEXT tile (two columns each, the same summation order as a
+// ray-at-a-time loop) while the current one executes, into the half of a double buffer the epilogue copies from at layer 1.
+__device__ __forceinline__ void view_bias(const TcParams& p, int ray, int gt, float* __restrict__ dst) {
+  const float* __restrict__ enc = p.cond + (size_t)ray * p.cond_dim;
+  const float* __restrict__ w = p.params + p.off_wview;
+  float v0 = __ldg(p.params + p.off_bcond + gt), v1 = __ldg(p.params + p.off_bcond + gt + 64);
+  for (int i = 0; i < p.cond_dim; ++i) {
+    const float c = __ldg(enc + i);
+    v0 = fmaf(c, __ldg(w + i * 128 + gt), v0);
+    v1 = fmaf(c, __ldg(w + i * 128 + gt + 64), v1);
+  }
+  dst[gt] = v0;
+  dst[gt + 64] = v1;
 }
 
 template <int W, bool SAVE>
@@ -406,17 +423,23 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     }
   } else if (warp == 2 || warp == 3) {
     if (!p.gen) {
-      // ===== feature-tile loader: the next tile's features arrive while the layers after the skip layer run =====
-      if (warp == 2 && lane == 0) {
-        uint32_t par = 0;
-        for (int tile = blockIdx.x; more(tile); tile += gridDim.x) {
-          mbar_wait(bar_inp_empty, par ^ 1);
+      // ===== feature-tile loader: the next tile's features arrive while the layers after the skip layer run; the 64 threads
+      // also form the next tile's view bias =====
+      uint32_t par = 0;
+      int it2 = 0;
+      for (int tile = blockIdx.x; more(tile); tile += gridDim.x, ++it2) {
+        const int tcl = min(tile, num_tiles - 1);
+        // every thread waits for the input tile to be free: that also says the tile before the previous one is past its
+        // layer 1, i.e. its half of the view-bias double buffer has been read
+        mbar_wait(bar_inp_empty, par ^ 1);
+        view_bias(p, p.ray_index ? p.ray_index[tcl] : tcl, threadIdx.x - 64, s_vbias + 128 + (it2 & 1) * 128);
+        asm volatile("bar.sync 3, 64;" ::: "memory");        // the row is complete before the tile is announced
+        if (threadIdx.x == 64) {
           mbar_arrive_expect_tx(bar_inp_full, kInpBytes);
-          bulk_g2s(sbase + C::OFF_INP, p.feat + (size_t)min(tile, num_tiles - 1) * kInpBytes, kInpBytes, bar_inp_full);
-          par ^= 1;
+          bulk_g2s(sbase + C::OFF_INP, p.feat + (size_t)tcl * kInpBytes, kInpBytes, bar_inp_full);
         }
+        par ^= 1;
       }
-      __syncwarp();
     } else {
       // ===== feature-tile GENERATOR (N1): 64 threads, two samples each; the ray-march of raymarch.cu's bf16 path, written
       // straight into the SWIZZLE_128B A-operand image in shared memory.  It runs while the layers after the skip layer of the
@@ -425,10 +448,12 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       const bool weighted = (p.rm_flags & DURF_RM_WEIGHTED) != 0;
       const bool sample = (p.rm_flags & DURF_RM_SAMPLE) != 0;
       uint32_t par = 0;
-      for (int tile = blockIdx.x; more(tile); tile += gridDim.x) {
+      int it2 = 0;
+      for (int tile = blockIdx.x; more(tile); tile += gridDim.x, ++it2) {
         const bool valid = tile < num_tiles;
         const int tcl = min(tile, num_tiles - 1);
         const int ray = p.ray_index ? p.ray_index[tcl] : tcl;
+        view_bias(p, ray, gt, s_vbias + 128 + (it2 & 1) * 128);       // announced with the tile (inp_full below)
         const float o[3] = {p.g_origins[3 * ray], p.g_origins[3 * ray + 1], p.g_origins[3 * ray + 2]};
         const float d[3] = {p.g_dirs[3 * ray], p.g_dirs[3 * ray + 1], p.g_dirs[3 * ray + 2]};
         const float radius = p.g_radii[ray];
@@ -519,13 +544,10 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       }
     };
     // per-ray bias of the condition layer (b + W_view^T enc(viewdir), obbpose_model.py:343-350): fetched a tile ahead
-    float vb_next = (ch == 0 && (int)blockIdx.x < num_tiles) ? p.vbias[(size_t)blockIdx.x * 128 + row] : 0.f;
-    for (int tile = blockIdx.x; more(tile); tile += gridDim.x) {
+    int it_e = 0;
+    for (int tile = blockIdx.x; more(tile); tile += gridDim.x, ++it_e) {
       const bool valid = tile < num_tiles;
       const int ray = !valid ? -1 : (p.ray_index ? p.ray_index[tile] : tile);
-      const float vb_mine = vb_next;
-      const int tile_next = tile + (int)gridDim.x;
-      vb_next = (ch == 0 && tile_next < num_tiles) ? p.vbias[(size_t)tile_next * 128 + row] : 0.f;
       float den = 0.f;
       float rgb[3] = {0.f, 0.f, 0.f};
       for (int g = 0; g < p.G; ++g) {
@@ -533,7 +555,9 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
           asm volatile("bar.sync 1, 256;" ::: "memory");   // s_part of the previous tile is complete; its s_vbias readers are done
           if (ch == 0) {
             if (ray_prev >= 0) flush_prev();
-            s_vbias[row] = vb_mine;
+            // this tile's view bias: formed by warps 2-3 before they announced the tile's input (inp_full -> MMAs of layer 0 ->
+            // acc_full, which this thread has waited on)
+            s_vbias[row] = s_vbias[128 + (it_e & 1) * 128 + row];
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
@@ -721,39 +745,6 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-// Per-tile bias of the condition layer: vbias[m][j] = b_cond[j] + sum_i enc(viewdir of ray m)[i] * W_cond[width + i][j].
-// The view direction is constant along a ray, so these 27 input columns never occupy tensor-core K.
-__global__ void __launch_bounds__(128)
-cond_bias_kernel(int M, const int32_t* __restrict__ count, const int32_t* __restrict__ ray_index, const float* __restrict__ cond,
-                 int cond_dim, const float* __restrict__ w_view, const float* __restrict__ b_cond, float* __restrict__ vbias) {
-  constexpr int RB = 16;                      // rays per block iteration: their view encodings are staged in shared memory once
-  __shared__ float s_w[64 * 128];
-  __shared__ float s_c[RB][64];
-  const int n = count ? min(*count, M) : M;
-  for (int i = threadIdx.x; i < cond_dim * 128; i += blockDim.x) s_w[i] = w_view[i];
-  const int j = threadIdx.x;
-  const float b = b_cond[j];
-  for (int m0 = blockIdx.x * RB; m0 < n; m0 += gridDim.x * RB) {
-    __syncthreads();                          // s_w ready / previous iteration's s_c consumed
-    for (int i = threadIdx.x; i < RB * cond_dim; i += blockDim.x) {
-      const int r = i / cond_dim, c = i - r * cond_dim, m = m0 + r;
-      s_c[r][c] = m < n ? cond[(size_t)(ray_index ? ray_index[m] : m) * cond_dim + c] : 0.f;
-    }
-    __syncthreads();
-    float vb[RB];
-#pragma unroll
-    for (int r = 0; r < RB; ++r) vb[r] = b;
-    for (int i = 0; i < cond_dim; ++i) {      // same summation order per output as a ray-at-a-time loop
-      const float w = s_w[i * 128 + j];
-#pragma unroll
-      for (int r = 0; r < RB; ++r) vb[r] = fmaf(s_c[r][i], w, vb[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < RB; ++r)
-      if (m0 + r < n) vbias[(size_t)(m0 + r) * 128 + j] = vb[r];
-  }
-}
-
 // fp32 parameter blob -> bf16 weight image: for every GEMM layer, N half and K block (the order the kernel
 // consumes them) one 128 x 64 K-major SWIZZLE_128B block of 16 KB.  One thread per 16-byte piece.
 constexpr int kMaxBlocks = 192;
@@ -889,7 +880,7 @@ int mlp_tc_pack(cudaStream_t st, const DurfMlpTopology& t, const float* params, 
 bool mlp_tc_bwd_supported(const DurfMlpTopology& t);
 int mlp_tc_saved_blocks(const DurfMlpTopology& t);
 
-size_t mlp_tc_workspace_bytes(const DurfMlpTopology& t, int64_t M) { return tc_supported(t) ? (size_t)M * 128 * sizeof(float) : 0; }
+size_t mlp_tc_workspace_bytes(const DurfMlpTopology&, int64_t) { return 0; }      // the tensor-core forward needs no workspace
 
 int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a) {
   const DurfMlpTopology& t = a.topo;
@@ -908,22 +899,14 @@ int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a) {
   }
   DURF_REQUIRE(a.saved == nullptr || mlp_tc_bwd_supported(t), DURF_E_UNSUPPORTED,
                "durf_mlp_fwd(bf16): activation saving needs a topology with a tensor-core backward");
-  const size_t need = mlp_tc_workspace_bytes(t, a.M);
-  DURF_REQUIRE(a.workspace && a.workspace_bytes >= need, DURF_E_WORKSPACE, "durf_mlp_fwd(bf16): workspace %zu < %zu bytes",
-               a.workspace_bytes, need);
   TcParams P;
   build_sched(t, P, (t.width == 256 && a.saved == nullptr) ? 4 : 2);      // = TcCfg<W, SAVE>::SKB
-  P.vbias = (const float*)a.workspace;
   P.saved = (uint8_t*)a.saved;
   P.saved_blocks_per_tile = mlp_tc_saved_blocks(t);
   P.masks = P.saved ? reinterpret_cast<uint32_t*>(P.saved + (size_t)a.M * P.saved_blocks_per_tile * kBlockBytes) : nullptr;
   {
     MlpLayout L(t);
-    const int grid_b = (a.M + 15) / 16 < 148 * 8 ? (a.M + 15) / 16 : 148 * 8;
-    cond_bias_kernel<<<grid_b, 128, 0, st>>>(a.M, a.count, a.ray_index, a.cond, t.cond_dim,
-                                             a.params + L.w_off[t.depth + 2] + (size_t)t.width * t.cond_width,
-                                             a.params + L.b_off[t.depth + 2], (float*)a.workspace);
-    DURF_CHECK_LAUNCH("durf_mlp_fwd(bf16): cond_bias");
+    P.off_bcond = (int)L.b_off[t.depth + 2];      // the per-tile view bias is formed inside the kernel (view_bias): no workspace
   }
   P.gen = rm ? 1 : 0;
   P.feat_out = nullptr;

@@ -76,8 +76,8 @@ def test_size_queries_are_host_functions_and_consistent():
             assert lib.durf_mlp_saved_bytes(C.byref(t), _lib.PREC_BF16, M, 128) == want
             # backward workspace = the dZ tile records, same shape as the saved activations
             assert lib.durf_mlp_workspace_bytes(C.byref(t), _lib.PREC_BF16, M, 128, 1) == M * blocks * 16384
-            # inference workspace = the per-tile view bias [M,128] fp32
-            assert lib.durf_mlp_workspace_bytes(C.byref(t), _lib.PREC_BF16, M, 128, 0) == M * 128 * 4
+            # the tensor-core forward needs no workspace (the per-tile view bias is formed inside the kernel)
+            assert lib.durf_mlp_workspace_bytes(C.byref(t), _lib.PREC_BF16, M, 128, 0) == 0
         assert lib.durf_mlp_packed_bytes(C.byref(t)) > 0
     odd = _lib.MlpTopology(60, 192, 8, 4, 27, 128)          # width the tensor-core path does not implement
     assert lib.durf_mlp_saved_bytes(C.byref(odd), _lib.PREC_BF16, 4, 128) == 0
