@@ -1,5 +1,6 @@
-"""Host-side mirror of the reference's CARLA loader (internal/obbpose_dataset.py:44-832, class `Carla`, the loader
-`configs/carla_dyn.gin` selects): the on-disk scene -> the batch dicts `train_step` / `render_image` consume.
+"""Host-side mirror of the reference's three loaders (internal/obbpose_dataset.py:44-832 class `Carla`, the loader
+`configs/carla_dyn.gin` selects; :833-1460 `Carla_Seq`; :1461-2087 `Waymo`, `configs/waymo.gin`): the on-disk scene -> the
+batch dicts `train_step` / `render_image` consume.
 
     <data_dir>/images_<factor>/*.png|jpg   RGB(A) frames, 5 cameras per timestep, natural file order
     <data_dir>/poses_bounds.npy            [n, 17]: 3x5 LLFF pose (rotation | translation | h, w, focal) + 2 depth bounds
@@ -47,6 +48,11 @@ class Carla:
     CAMERAS_PER_TIMESTEP = 5          # FRONT, FRONT_LEFT, SIDE_LEFT, FRONT_RIGHT, SIDE_RIGHT (:515)
     SCENE_SCALE = 5.0                 # far plane 1000 -> 200 (:446)
     SEED = 20201473                   # :208
+    I_TEST = (10, 11)                 # the hard-coded hold-out (:538)
+    EXT_DIVISOR = 5.0                 # box extents are half extents in scene units (:474)
+    SKY_VALUE = 0.995                 # "large distance but not infinity" (:596)
+    RENDER_SPLIT_IS_TRAIN = True      # split == 'render' uses the training frames (:544)
+    POSE_COLUMNS = 17                 # 15 pose + 2 depth bounds
 
     def __init__(self, split: str, data_dir: str, config: Config):
         if split not in ('train', 'test', 'render'):
@@ -96,8 +102,9 @@ class Carla:
         images = np.array([np.array(Image.open(os.path.join(imgdir, f)), dtype=np.float32)[:, :, :3] / 255. for f in files])
 
         poses_arr = np.load(os.path.join(self.data_dir, 'poses_bounds.npy'))
-        poses = poses_arr[:, :-2].reshape([-1, 3, 5]).transpose([1, 2, 0])
-        bds = poses_arr[:, -2:].transpose([1, 0])
+        poses = poses_arr[:, :15].reshape([-1, 3, 5]).transpose([1, 2, 0])
+        bds = poses_arr[:, 15:17].transpose([1, 0])
+        principal_point = poses_arr[:, 17:] * 1. / factor if self.POSE_COLUMNS > 17 else None      # Waymo: (cx, cy) per frame
         if poses.shape[-1] != len(images):
             raise RuntimeError('Mismatch between imgs {} and poses {}'.format(len(images), poses.shape[-1]))
         masks3d = np.load(os.path.join(self.data_dir, '3D_boxes.npy'), allow_pickle=True).item()
@@ -134,7 +141,7 @@ class Carla:
             else:
                 rand_pose = np.concatenate([box_pose[:, :3, 3], yaw], axis=-1)
             obbpose = np.concatenate([box_pose[:, :3, 3], yaw], axis=-1)
-            box_ext = box_ext / self.SCENE_SCALE
+            box_ext = box_ext / self.EXT_DIVISOR
         rel_pose, can_pose = {}, None
         for i, key in enumerate(centers):
             ts, car, _ = key.split('_')
@@ -162,22 +169,22 @@ class Carla:
                                       "(obbpose_dataset.py:693-700) and cannot run; configs/carla_dyn.gin sets spherify = True")
         self.spherify = True
 
-        i_test = np.array([10, 11])                                                   # :538
-        i_train = np.array([i for i in np.arange(len(images)) if i not in i_test])
-        indices = i_test if self.split == 'test' else i_train
+        i_train, i_test = self._hold_out(len(images), config)
+        if self.split == 'test':
+            indices = i_test
+        elif self.split == 'render' and not self.RENDER_SPLIT_IS_TRAIN:
+            indices = np.sort(np.concatenate([i_train, i_test]))
+        else:
+            indices = i_train
         images, depth, sky, poses, masks2d = images[indices], depth[indices], sky[indices], poses[indices], masks2d[indices]
         self.timesteps = timesteps[indices]
         self.rel_poses, self.box_pose = rel_pose, masks3d
-        ids: List = []
-        for u in masks2d:
-            for i in np.unique(u):
-                if i != 0 and i not in ids:
-                    ids.append(i)
-        self.obj_ids = np.array(ids)
+        self.principal_point = None if principal_point is None else principal_point[indices]
+        self.obj_ids = self._object_ids(masks2d)
         timestep_batches = config.batching == 'timestep'
         self.images = list(images)
         self.depth = [np.where(d > 0.0, d / self.SCENE_SCALE, d).astype(d.dtype) for d in depth]
-        self.sky_mask = [np.where(s > 0.0, np.asarray(0.995, s.dtype), s) for s in sky]
+        self.sky_mask = [np.where(s > 0.0, np.asarray(self.SKY_VALUE, s.dtype), s) for s in sky]
         self.masks2d = list(masks2d)
         if timestep_batches:
             self.depth = [d[..., None] for d in self.depth]
@@ -187,6 +194,20 @@ class Carla:
         self.focal, self.h, self.w = poses[:, -1, -1], poses[:, 0, -1], poses[:, 1, -1]
         self.resolution = self.h * self.w
         self.n_examples = len(self.images)
+
+    def _hold_out(self, n: int, config: Config):
+        """(training frames, held-out frames): frames 10 and 11 are held out (:538-540)."""
+        i_test = np.array(self.I_TEST)
+        return np.array([i for i in np.arange(n) if i not in i_test]), i_test
+
+    def _object_ids(self, masks2d):
+        """:567-574: the instance ids that occur in the selected frames' 2D masks, in order of first appearance."""
+        ids: List = []
+        for u in masks2d:
+            for i in np.unique(u):
+                if i != 0 and i not in ids:
+                    ids.append(i)
+        return np.array(ids)
 
     def _recenter_poses(self, poses):
         """:709-720 (the original NeRF recentring): world := the average camera's frame."""
@@ -214,7 +235,8 @@ class Carla:
         for i in range(len(self.images)):
             w, h, f = self.w[i], self.h[i], self.focal[i]
             x, y = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32), indexing='xy')
-            cam_dirs = np.stack([(x - w * 0.5) / f, -(y - h * 0.5) / f, -np.ones_like(x)], axis=-1)
+            cx, cy = (w * 0.5, h * 0.5) if self.principal_point is None else self.principal_point[i]
+            cam_dirs = np.stack([(x - cx) / f, -(y - cy) / f, -np.ones_like(x)], axis=-1)
             directions = np.squeeze((cam_dirs[..., None, :] * self.camtoworlds[i, :3, :3]).sum(axis=-1))
             origins = np.broadcast_to(self.camtoworlds[i, :3, -1], directions.shape)
             viewdirs = directions / np.linalg.norm(directions, axis=-1, keepdims=True)
@@ -229,8 +251,9 @@ class Carla:
     def camera(self, i: int) -> Dict:
         """Pinhole parameters of image i for `obbpose_model.render_camera` / `ops.generate_rays`: the same rays as
         `self.rays[...][i]`, generated on the device (durf_generate_rays, image-centre variant: (x - w/2) / focal)."""
+        pp = None if self.principal_point is None else (float(self.principal_point[i, 0]), float(self.principal_point[i, 1]))
         return dict(c2w=self.camtoworlds[i], width=int(self.w[i]), height=int(self.h[i]), focal=float(self.focal[i]),
-                    near=float(self.near), far=float(self.far))
+                    near=float(self.near), far=float(self.far), principal_point=pp)
 
     def _flatten_time(self, x):
         """:235-253: flatten every image and pool the cameras of one timestep."""
@@ -267,11 +290,40 @@ class Carla:
                 'can': self._boxes(1, 'off', 6), 'ts': t - 1, 'target': self._boxes(t, 'center', 6)}
 
 
-dataset_dict = {'carla_dyn': Carla}
+class Waymo(Carla):
+    """internal/obbpose_dataset.py:1461-2087, the loader `configs/waymo.gin` selects.  The reference's class is a copy of `Carla`
+    with these differences, all of which are the class attributes and hooks below: `poses_bounds.npy` carries the principal
+    point (cx, cy) in two extra columns and the rays go through it (:1635-1637, 1882-1885); box extents are FULL extents
+    (:1731, / 10); the hold-out is frames 10 and 12 and the 'render' split is every frame (:1806-1813); the object ids are
+    1..n from the box dictionary, not from the 2D masks (:1828-1830); sky pixels become 0.975 (:1853)."""
+
+    I_TEST = (10, 12)
+    EXT_DIVISOR = 10.0
+    SKY_VALUE = 0.975
+    RENDER_SPLIT_IS_TRAIN = False
+    POSE_COLUMNS = 19
+
+    def _object_ids(self, masks2d):
+        last_ts = list(self.box_pose.keys())[-1].split('_')[0]
+        return np.arange(1, int(len(self.box_pose) / 3 / int(last_ts)) + 1)
+
+
+class Carla_Seq(Carla):
+    """internal/obbpose_dataset.py:833-1460 ('carla_seq'): a single-camera sequence.  The reference's class is a copy of `Carla`
+    with one frame per timestep (:1160-1161), every `llffhold`-th frame as the test split and ALL frames - the held-out ones
+    included - as the training split (:1175-1178)."""
+
+    CAMERAS_PER_TIMESTEP = 1
+
+    def _hold_out(self, n: int, config: Config):
+        return np.arange(n), np.arange(n)[::config.llffhold]
+
+
+dataset_dict = {'carla_dyn': Carla, 'carla_seq': Carla_Seq, 'waymo': Waymo}
 
 
 def get_dataset(split: str, train_dir: str, config: Config):
     """internal/obbpose_dataset.py:17-18."""
     if config.dataset_loader not in dataset_dict:
-        raise NotImplementedError(f"dataset_loader {config.dataset_loader!r}: only 'carla_dyn' (configs/carla_dyn.gin) is implemented")
+        raise NotImplementedError(f"dataset_loader {config.dataset_loader!r}: the reference has 'carla_dyn', 'carla_seq' and 'waymo'")
     return dataset_dict[config.dataset_loader](split, train_dir, config)

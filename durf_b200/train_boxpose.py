@@ -147,7 +147,7 @@ def main(argv=None) -> Dict:
             tb, cam = test.peek(), test.camera(0)
             rgb, dist, acc = render_camera(fn, cam['c2w'], cam['width'], min(args.render_rows, cam['height']), cam['focal'], cam['near'],
                                            cam['far'], None, torch.from_numpy(np.asarray(tb['ext'], np.float32)).to(dev), int(tb['ts']),
-                                           None, alpha_fn(state.step))
+                                           None, alpha_fn(state.step), principal_point=cam['principal_point'])
         else:
             rgb, dist, acc = render_camera(fn, dataset.c2w[0], S.WAYMO_W, args.render_rows, S.FOCAL, config.near, config.far, None,
                                            torch.from_numpy(dataset.ext).to(dev), 0, None, alpha_fn(state.step))

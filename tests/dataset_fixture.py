@@ -1,4 +1,4 @@
-"""A synthetic on-disk CARLA scene in the layout internal/obbpose_dataset.py reads (test infrastructure): 3 timesteps x 5
+"""A synthetic on-disk CARLA (or, with waymo=True, Waymo) scene in the layout internal/obbpose_dataset.py reads (test infrastructure): 3 timesteps x 5
 cameras of 12 x 16 pixels at factor 4, two cars, LIDAR depth with holes, sky masks, instance masks.  File names are
 zero-padded so that natural and lexicographic order agree (the test-only natsort stand-in sorts lexicographically)."""
 import os
@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 
-def make_scene(root: str, T: int = 3, cams: int = 5, H: int = 12, W: int = 16, factor: int = 4, seed: int = 5) -> str:
+def make_scene(root: str, T: int = 3, cams: int = 5, H: int = 12, W: int = 16, factor: int = 4, seed: int = 5,
+               waymo: bool = False) -> str:
     from PIL import Image
     rng = np.random.default_rng(seed)
     n = T * cams
@@ -22,7 +23,10 @@ def make_scene(root: str, T: int = 3, cams: int = 5, H: int = 12, W: int = 16, f
         t = rng.uniform(-20, 20, size=3) + np.array([0, 0, 5.0 * (i // cams)])
         hwf = np.array([H * factor, W * factor, 50.0 * factor])
         p = np.concatenate([rot, t[:, None], hwf[:, None]], 1)
-        poses.append(np.concatenate([p.reshape(-1), [1.0, 400.0]]))
+        row = np.concatenate([p.reshape(-1), [1.0, 400.0]])
+        if waymo:      # two more columns: the principal point (cx, cy) in full-resolution pixels (obbpose_dataset.py:1637)
+            row = np.concatenate([row, [W * factor * 0.5 + rng.uniform(-3, 3), H * factor * 0.5 + rng.uniform(-3, 3)]])
+        poses.append(row)
     np.save(os.path.join(root, 'poses_bounds.npy'), np.array(poses))
     boxes = {}
     for ts in range(1, T + 1):

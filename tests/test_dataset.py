@@ -2,7 +2,8 @@
 
 `test_loader_equals_the_live_reference` (only where /root/reference exists) runs internal/obbpose_dataset.py unmodified on the
 test-only jax / gin stand-in over a synthetic on-disk scene and compares every array of the first training batches and of the
-held-out frames, for the shipped configuration and with box / yaw noise enabled.  The same batches are committed as
+held-out frames, for the shipped CARLA configuration, with box / yaw noise enabled, for the Waymo loader (configs/waymo.gin, with and
+without its box noise) and for the single-camera sequence loader.  The same batches are committed as
 tests/golden/ref_dataset.npz (written by this test's generator mode: `python tests/test_dataset.py --write`) so that the
 comparison also runs where the reference is absent."""
 import os
@@ -16,14 +17,26 @@ import dataset_fixture as F
 import refshim_loader as RL
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_dataset.npz')
-CASES = {'shipped': dict(), 'noisy': dict(random_box=True, random_yaw=True)}
+# case -> (loader, Config overrides on top of the loader's shipped .gin)
+CASES = {'shipped': ('carla_dyn', dict()), 'noisy': ('carla_dyn', dict(random_box=True, random_yaw=True)),
+         'waymo': ('waymo', dict(random_box=False)), 'waymo_shipped': ('waymo', dict()),      # configs/waymo.gin: random_box = True
+         'seq': ('carla_seq', dict(dataset_loader='carla_seq', llffhold=4))}                  # no .gin ships for it: carla_dyn.gin + loader
+GIN = {'carla_dyn': 'carla_dyn.gin', 'carla_seq': 'carla_dyn.gin', 'waymo': 'waymo.gin'}
+# values of the reference's .gin files that differ from durf_b200.utils.Config's defaults (= configs/carla_dyn.gin)
+OURS_BASE = {'carla_dyn': dict(), 'carla_seq': dict(), 'waymo': dict(dataset_loader='waymo', far=40.0, random_box=True)}
+
+
+def _scene(path, loader):
+    if loader == 'carla_seq':
+        return F.make_scene(path, T=13, cams=1)
+    return F.make_scene(path, waymo=loader == 'waymo')
 N_TRAIN, N_TEST = 3, 2
 
 
 def _splits(overrides):
     """With box / yaw noise only the training split is reproducible in the reference: `_train_init` seeds the global numpy
     generator before the noise is drawn (:208), `_test_init` does not."""
-    return (('train', N_TRAIN),) if overrides.get('random_box') else (('train', N_TRAIN), ('test', N_TEST))
+    return (('train', N_TRAIN),) if overrides.get('random_box') else (('train', N_TRAIN), ('test', N_TEST), ('render', 1))
 
 
 def _flatten(prefix, batch, out):
@@ -35,12 +48,13 @@ def _flatten(prefix, batch, out):
             out[f'{prefix}/{k}'] = np.asarray(v)
 
 
-def _ours(root, overrides):
+def _ours(root, loader, overrides):
     from durf_b200.obbpose_dataset import get_dataset
     from durf_b200.utils import Config
+    kw = dict(OURS_BASE[loader], **overrides)
     out = {}
-    for split, n in _splits(overrides):
-        ds = get_dataset(split, root, Config(**overrides))
+    for split, n in _splits(kw):
+        ds = get_dataset(split, root, Config(**kw))
         first = ds.peek()
         for i in range(n):
             b = next(ds)
@@ -50,18 +64,19 @@ def _ours(root, overrides):
     return out
 
 
-def _reference(root, overrides):
-    """The reference's Carla loader (a thread filling a queue from the GLOBAL numpy generator), run live on the stand-in."""
+def _reference(root, loader, overrides):
+    """The reference's loader class (a thread filling a queue from the GLOBAL numpy generator), run live on the stand-in."""
     import importlib
     ref = RL.load_reference()
     ds_mod = importlib.import_module('internal.obbpose_dataset')
-    ref.gin.parse_config_file(os.path.join(RL.REFERENCE_ROOT, 'configs', 'carla_dyn.gin'))
+    ref.gin.parse_config_file(os.path.join(RL.REFERENCE_ROOT, 'configs', GIN[loader]))
     cfg = ref.utils.Config()
     for k, v in overrides.items():
         setattr(cfg, k, v)
+    kw = dict(OURS_BASE[loader], **overrides)
     out = {}
-    for split, n in _splits(overrides):
-        ds = ds_mod.Carla(split, root, cfg)
+    for split, n in _splits(kw):
+        ds = ds_mod.dataset_dict[loader](split, root, cfg)
         for i in range(n):
             _flatten(f'{split}{i}', ds.queue.get(timeout=60), out)
         # the loader thread keeps drawing from np.random; it is a daemon thread and dies with the process
@@ -81,16 +96,17 @@ def _compare(got, want, what):
 
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_loader_equals_the_committed_reference_batches(case, tmp_path):
-    root = F.make_scene(str(tmp_path / 'scene'))
+    loader, overrides = CASES[case]
+    root = _scene(str(tmp_path / 'scene'), loader)
     want = {k[len(case) + 1:]: v for k, v in np.load(GOLDEN).items() if k.startswith(case + '/')}
-    _compare(_ours(root, CASES[case]), want, case)
+    _compare(_ours(root, loader, overrides), want, case)
 
 
 @pytest.mark.skipif(not RL.reference_available(), reason="needs /root/reference (absent on the GPU box)")
 def test_loader_equals_the_live_reference(tmp_path):
-    root = F.make_scene(str(tmp_path / 'scene'))
-    for case, overrides in CASES.items():
-        _compare(_ours(root, overrides), _reference(root, overrides), case)
+    for case, (loader, overrides) in CASES.items():
+        root = _scene(str(tmp_path / case), loader)
+        _compare(_ours(root, loader, overrides), _reference(root, loader, overrides), case)
 
 
 def test_loader_contract(tmp_path):
@@ -109,7 +125,10 @@ def test_loader_contract(tmp_path):
     with pytest.raises(NotImplementedError):
         get_dataset('train', root, Config(spherify=False))
     with pytest.raises(NotImplementedError):
-        get_dataset('train', root, Config(dataset_loader='waymo'))
+        get_dataset('train', root, Config(dataset_loader='llff'))
+    wroot = F.make_scene(str(tmp_path / 'wscene'), waymo=True)
+    w = get_dataset('render', wroot, Config(dataset_loader='waymo', far=40.0))
+    assert w.size == 15 and w.camera(0)['principal_point'] is not None and get_dataset('test', wroot, Config(dataset_loader='waymo')).size == 2
     with pytest.raises(ValueError):
         get_dataset('train', str(tmp_path / 'missing'), Config())
 
@@ -118,10 +137,10 @@ if __name__ == '__main__' and '--write' in sys.argv:
     import tempfile
     assert RL.reference_available(), "the generator needs /root/reference"
     with tempfile.TemporaryDirectory() as d:
-        root = F.make_scene(os.path.join(d, 'scene'))
         blob = {}
-        for case, overrides in CASES.items():
-            for k, v in _reference(root, overrides).items():
+        for case, (loader, overrides) in CASES.items():
+            root = _scene(os.path.join(d, case), loader)
+            for k, v in _reference(root, loader, overrides).items():
                 blob[f'{case}/{k}'] = v
     np.savez_compressed(GOLDEN, **blob)
     print('wrote', GOLDEN, len(blob), 'arrays', os.path.getsize(GOLDEN), 'bytes')

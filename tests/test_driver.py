@@ -50,8 +50,11 @@ def test_driver_trains_from_an_on_disk_scene(tmp_path):
     from durf_b200 import ops
     from durf_b200.obbpose_dataset import get_dataset
     from durf_b200.utils import Config
-    test = get_dataset("test", scene, Config())
-    cam = test.camera(0)
-    dev_rays = ops.generate_rays(cam["c2w"], cam["width"], cam["height"], cam["focal"], cam["near"], cam["far"])
-    for name, host, dev in zip(dev_rays._fields, test.rays, dev_rays):
-        np.testing.assert_allclose(dev.cpu().numpy().reshape(host[0].shape), host[0], rtol=1e-6, atol=1e-6, err_msg=name)
+    wscene = F.make_scene(str(tmp_path / "wscene"), waymo=True)
+    for root, cfg in ((scene, Config()), (wscene, Config(dataset_loader="waymo", far=40.0))):      # image centre / principal point
+        test = get_dataset("test", root, cfg)
+        cam = test.camera(0)
+        dev_rays = ops.generate_rays(cam["c2w"], cam["width"], cam["height"], cam["focal"], cam["near"], cam["far"],
+                                     principal_point=cam["principal_point"])
+        for name, host, dev in zip(dev_rays._fields, test.rays, dev_rays):
+            np.testing.assert_allclose(dev.cpu().numpy().reshape(host[0].shape), host[0], rtol=1e-6, atol=1e-6, err_msg=name)
