@@ -15,12 +15,15 @@
 //     and the same asm block carries the tcgen05.commit's (accumulator ready, ring stage free).
 // Warp roles (384 threads): warp 0 = weight producer (cp.async.bulk of pre-tiled, pre-swizzled bf16 chunks into an
 // mbarrier ring; in a CTA pair each CTA fetches half of a stage and multicasts it), warp 1 = MMA issuer (whole warp walks
-// the schedule, one elected lane issues), warp 2 = TMEM allocator + feature-tile loader, warp 3 idle,
+// the schedule, one elected lane issues), warps 2-3 = the input side: warp 2 allocates TMEM; with DurfMlpArgs.fused_raymarch
+// the 64 threads GENERATE the next tile's A operand in shared memory (sampling, conical-frustum Gaussian, contraction, IPE:
+// raymarch_device.cuh), otherwise one of them loads the tile image; in both cases they form the next tile's view bias,
 // warps 4-11 = epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter split the columns of a half).
 // The skip connection (obbpose_model.py:332-333) is an extra K block read from the still-resident input tile (smem,
 // ".ss" form); the view direction (constant along a ray) enters the condition layer as a per-tile fp32 bias
-// (b + W_view^T enc), so its 27 input columns never occupy tensor-core K; the density head (N=1) and the rgb head
-// (N=3) are dot products inside the epilogues.
+// (b + W_view^T enc, view_bias below), so its 27 input columns never occupy tensor-core K; the density head (N=1) and the
+// rgb head (N=3) are dot products inside the epilogues.  Training (SAVE) additionally stores every layer's bf16 activations,
+// 1-bit ReLU masks and the generated tile for the backward kernels (save_piece).
 #include <stdlib.h>
 
 #include "tc_common.cuh"

@@ -6,9 +6,12 @@
 //   stage 2+ : dZ_{g-1} = (dZ_g W_g[:width]^T) * [a_{g-1} > 0]      g = depth-1 .. 1
 // Same machinery as the forward: accumulators AND the bf16 dZ operands live in tensor memory (tcgen05.mma .ts), every
 // stage is issued as N-halves so the masking epilogue of one half overlaps the MMAs of the other, the transposed weight
-// image streams through a 3-stage ring of 64 KB chunks.  Every dZ (and dBott, dZ_cond) is also written to HBM as tile
-// images: they are the B operands of the weight-gradient kernel (mlp_tc_wgrad.cu).  The ReLU masks come from the
-// activations the forward pass saved.  For width 128 (BoxMLP) an optional last stage forms the input gradient
+// image streams through a ring of 32 KB stages.  Every dZ (and dBott, dZ_cond) is also written to HBM as block images
+// (per-warp 4 KB pieces: shared-memory staging + cp.async.bulk stores): they are the B operands of the weight-gradient
+// kernel (mlp_tc_wgrad.cu).  Every ReLU mask is a 1-bit word written by the forward pass (the saved activations themselves
+// are not read here); the next tile's upstream gradients and mask words are prefetched under the last stage.  With
+// `tile_done` counters (durf_mlp_bwd_data) warp 3 publishes every completed dZ piece for a weight-gradient kernel running
+// concurrently on other SMs.  For width 128 (BoxMLP) an optional last stage forms the input gradient
 //   dX = dZ_0 W_0^T + dZ_skip W_skip[width:]^T   (64 columns, fp32 rows)
 // that the box-pose path needs; dZ_skip waits in a third TMEM buffer.  The background branch needs no input gradient
 // (its samples depend on no parameter).

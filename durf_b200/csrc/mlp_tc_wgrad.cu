@@ -2,11 +2,12 @@
 // (obbpose_model.py:326-353, 390-417 under jax.value_and_grad, train_boxpose.py:251)
 //     dW[in, out] += A^T dZ        db[out] += column sums of dZ
 // summed over all samples.  A (the layer's bf16 input activations, saved by the forward kernel) and dZ (the bf16
-// pre-activation gradients written by the dgrad kernel) live in HBM as per-tile block images: 128 samples x 64 features,
-// 128-byte rows, SWIZZLE_128B.  For wgrad the SAMPLE index is the contraction index, so the very same images are
+// pre-activation gradients written by the dgrad kernel) live in HBM as per-tile block images: 64-feature blocks of
+// 128-byte rows, SWIZZLE_128B, a layer's record ordered [sample half][block][64 rows] so that the 64 samples of all its
+// blocks are one contiguous 32 KB piece.  For wgrad the SAMPLE index is the contraction index, so the very same images are
 // MN-major tcgen05 operands (the 128-byte rows run along M / N, the 8-row groups along K): no transpose is ever made.
 //
-// The work is a list of jobs (one per weight matrix).  Every CTA is bound to ONE job and a contiguous share of the tiles
+// The work is a list of jobs (one per weight matrix).  Every CTA is bound to ONE job and takes that job's tiles round-robin
 // (the host splits the SMs over the jobs in proportion to the bytes a job streams per tile): the job's [in <= 256, out <= 256]
 // fp32 accumulator sits in TMEM (<= 512 columns) for the whole kernel while the CTA streams its tiles through a 3-stage
 // ring (64 samples of A and dZ per stage, cp.async.bulk + mbarrier), and is added to the global gradient ONCE at the end
