@@ -217,8 +217,8 @@ def mlp(params, features, cond, topo, num_rays, num_samples=128, precision=PREC_
     acc = into is not None
     rgb0, den0 = into if acc else (jnp.zeros((B, num_samples, 3), f), jnp.zeros((B, num_samples), f))
     attrs = dict(_topo_attrs(topo), precision=int(precision), num_rays=int(num_rays), num_samples=int(num_samples))
-    ws_fwd, saved_bytes = _sizes(topo, precision, num_rays, num_samples, True)
-    ws_bwd, _ = _sizes(topo, precision, num_rays, num_samples, True)
+    ws_fwd, _ = _sizes(topo, precision, num_rays, num_samples, False)          # the tensor-core forward needs none (16 B placeholder)
+    ws_bwd, saved_bytes = _sizes(topo, precision, num_rays, num_samples, True)    # backward: the dZ records; saved: activations + masks
     n_params = params.shape[0]
 
     def call_fwd(p, x, training):
