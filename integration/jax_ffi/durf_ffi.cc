@@ -172,6 +172,41 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(DurfMlpFwd, MlpFwdImpl,
                                   .Attr<int32_t>("num_rays").Attr<int32_t>("num_samples").Attr<int32_t>("accumulate")
                                   .Ret<F32>().Ret<F32>().Ret<U8>().Ret<U8>());
 
+// The same forward with the ray-march FUSED into the kernel (DurfMlpArgs.fused_raymarch, BF16 only): the MLP kernel
+// generates its input tiles from the rays (mip.py:155-282, mip360.py:47-79 inside K2), so no feature tensor exists between the
+// two reference calls.  t_vals is an operand aliased to the third result (written when DURF_RM_SAMPLE, else read);
+// `features_out` (0 elements = not wanted) receives the generated bf16 tiles for the backward handler.
+static ffi::Error MlpFwdFusedImpl(cudaStream_t stream, F32 origins, F32 dirs, F32 radii, F32 near, F32 far, F32 t_rand, F32 ray_mult,
+                                  F32 t_vals_in, F32 cond, F32 params, U8 packed, S32 ray_index, S32 count, F32 raw_rgb_in,
+                                  F32 raw_density_in, int32_t in_dim, int32_t width, int32_t depth, int32_t skip, int32_t cond_dim,
+                                  int32_t cond_width, int32_t num_rays, int32_t min_deg, int32_t max_deg, int32_t flags, float alpha,
+                                  int32_t accumulate, RF32 raw_rgb, RF32 raw_density, RF32 t_vals, ffi::Result<ffi::AnyBuffer> features_out,
+                                  RU8 saved) {
+  (void)t_vals_in; (void)raw_rgb_in; (void)raw_density_in;
+  DurfRaymarchArgs r{};
+  FillRaymarch(r, origins, dirs, radii, near, far, t_rand, ray_mult, ray_index, count, 128, min_deg, max_deg, flags, alpha);
+  r.t_vals = t_vals->typed_data();
+  DurfMlpArgs a{};
+  a.topo = Topo(in_dim, width, depth, skip, cond_dim, cond_width);
+  a.precision = DURF_PREC_BF16; a.M = num_rays; a.N = 128;
+  a.features = features_out->element_count() ? features_out->untyped_data() : nullptr;
+  a.cond = cond.typed_data(); a.params = params.typed_data(); a.packed = packed.untyped_data();
+  a.ray_index = OrNull(ray_index); a.count = OrNull(count); a.accumulate = accumulate;
+  a.raw_rgb = raw_rgb->typed_data(); a.raw_density = raw_density->typed_data();
+  a.saved = saved->element_count() ? saved->untyped_data() : nullptr;
+  a.fused_raymarch = &r;
+  return Check(durf_mlp_fwd(stream, &a));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DurfMlpFwdFused, MlpFwdFusedImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>()
+                                  .Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<F32>().Arg<U8>().Arg<S32>().Arg<S32>()
+                                  .Arg<F32>().Arg<F32>()
+                                  .Attr<int32_t>("in_dim").Attr<int32_t>("width").Attr<int32_t>("depth").Attr<int32_t>("skip")
+                                  .Attr<int32_t>("cond_dim").Attr<int32_t>("cond_width").Attr<int32_t>("num_rays")
+                                  .Attr<int32_t>("min_deg").Attr<int32_t>("max_deg").Attr<int32_t>("flags").Attr<float>("alpha")
+                                  .Attr<int32_t>("accumulate")
+                                  .Ret<F32>().Ret<F32>().Ret<F32>().Ret<ffi::AnyBuffer>().Ret<U8>());
+
 // Backward: d raw_rgb, d raw_density -> d params (zero-initialised operand aliased to the result: the library accumulates)
 // and, for the box-pose path, d features fp32 [M*N, in_dim] (0-sized result = not wanted).
 static ffi::Error MlpBwdImpl(cudaStream_t stream, ffi::AnyBuffer features, F32 cond, F32 params, U8 packed, S32 ray_index, S32 count,

@@ -7,6 +7,7 @@ exposes differentiable functions with the argument meaning of the reference's ca
     DurfObbFrontendFwd              DurfObbFrontendBwd      obb_frontend        (d box_centers[ts])
     DurfRaymarchFwd (fp32 / bf16)   DurfRaymarchBwd         encode_object_rays  (d origins_s, d dirs_s: the box-pose path)
     DurfMlpFwd                      DurfMlpBwd              mlp                 (d params, d features)
+    DurfMlpFwdFused (N1)            DurfMlpBwd              background_mlp_fused (d params; the rays carry no gradient)
     DurfCompositeFwd                DurfCompositeBwd        volumetric_rendering_raw (d raw_rgb, d raw_density, d dirs_s)
     DurfResampleFwd                 - (stop_gradient, mip.py:413-414)           resample_along_rays_t
     DurfViewdirEnc, DurfCompactHits, DurfMlpPack            - (no differentiable inputs)
@@ -34,6 +35,7 @@ HANDLERS = {
     "DurfViewdirEnc": (1, 1, 1),
     "DurfMlpPack": (1, 6, 1),
     "DurfMlpFwd": (8, 10, 4),
+    "DurfMlpFwdFused": (15, 12, 5),
     "DurfMlpBwd": (10, 9, 3),
     "DurfCompositeFwd": (4, 3, 6),
     "DurfCompositeBwd": (8, 3, 3),
@@ -248,6 +250,54 @@ def mlp(params, features, cond, topo, num_rays, num_samples=128, precision=PREC_
 
     run.defvjp(run_fwd, run_bwd)
     return run(params, features)
+
+
+def background_mlp_fused(params, packed, rays_o, rays_d, radii, viewdirs_enc, topo, *, t_vals=None, near=None, far=None, t_rand=None,
+                         ray_mult=None, contract=True, min_deg=0, max_deg=10):
+    """SURVEY N1 from JAX: sample_along_rays / cast_rays / new_space / integrated_pos_enc AND the background MLP in ONE custom
+    call (the tcgen05 kernel generates its input tiles; no feature tensor exists in HBM at inference).  Level 0: pass near / far
+    (and t_rand for stratified sampling), t_vals is produced; resampled levels: pass t_vals.  Returns (raw_rgb, raw_density,
+    t_vals); differentiable w.r.t. `params` (the background's samples depend on no parameter)."""
+    import jax
+    import jax.numpy as jnp
+    f = jnp.float32
+    B, N = rays_o.shape[0], 128
+    e, ei = jnp.zeros((0,), f), jnp.zeros((0,), jnp.int32)
+    sampling = t_vals is None
+    flags = (RM_SAMPLE if sampling else 0) | (RM_RANDOMIZED if (sampling and t_rand is not None) else 0) | (RM_CONTRACT if contract else 0)
+    tv0 = jnp.zeros((B, N + 1), f) if sampling else t_vals
+    attrs = dict(_topo_attrs(topo), num_rays=B, min_deg=int(min_deg), max_deg=int(max_deg), flags=int(flags), alpha=0.0, accumulate=0)
+    ws_bwd, saved_bytes = _sizes(topo, PREC_BF16, B, N, True)
+    n_params = params.shape[0]
+
+    def call(p, training):
+        outs = (jax.ShapeDtypeStruct((B, N, 3), f), jax.ShapeDtypeStruct((B, N), f), jax.ShapeDtypeStruct((B, N + 1), f),
+                jax.ShapeDtypeStruct((B if training else 0, 128 * 64), jnp.bfloat16),
+                jax.ShapeDtypeStruct((saved_bytes if training else 0,), jnp.uint8))
+        return jax.ffi.ffi_call("DurfMlpFwdFused", outs, input_output_aliases={7: 2, 13: 0, 14: 1})(
+            rays_o, rays_d, radii.reshape(-1), e if near is None else near.reshape(-1), e if far is None else far.reshape(-1),
+            e if t_rand is None else t_rand, e if ray_mult is None else ray_mult, tv0, viewdirs_enc, p, packed, ei, ei,
+            jnp.zeros((B, N, 3), f), jnp.zeros((B, N), f), **attrs)
+
+    @jax.custom_vjp
+    def run(p):
+        r = call(p, False)
+        return r[0], r[1], r[2]
+
+    def run_fwd(p):
+        r = call(p, True)
+        return (r[0], r[1], r[2]), (p, r[3], r[4])
+
+    def run_bwd(res, cts):
+        p, tiles, saved = res
+        outs = (jax.ShapeDtypeStruct((n_params,), f), jax.ShapeDtypeStruct((0,), f), jax.ShapeDtypeStruct((ws_bwd,), jnp.uint8))
+        d_p, _, _ = jax.ffi.ffi_call("DurfMlpBwd", outs, input_output_aliases={9: 0})(
+            tiles, viewdirs_enc, p, packed, ei, ei, saved, cts[0], cts[1], jnp.zeros((n_params,), f), **_topo_attrs(topo),
+            precision=PREC_BF16, num_rays=B, num_samples=N)
+        return (d_p,)
+
+    run.defvjp(run_fwd, run_bwd)
+    return run(params)
 
 
 # ---- K3 / K4 ---------------------------------------------------------------------------------------------------------
