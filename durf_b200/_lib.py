@@ -64,7 +64,8 @@ class MlpArgs(C.Structure):
                 ("features", C.c_void_p), ("cond", C.c_void_p), ("params", C.c_void_p), ("packed", C.c_void_p),
                 ("ray_index", C.c_void_p), ("count", C.c_void_p), ("accumulate", C.c_int32),
                 ("raw_rgb", C.c_void_p), ("raw_density", C.c_void_p), ("saved", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("fused_raymarch", C.c_void_p)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("fused_raymarch", C.c_void_p),
+                ("saved_tile_offset", C.c_int32), ("saved_total_tiles", C.c_int32)]
 
 
 class CompositeArgs(C.Structure):

@@ -924,9 +924,15 @@ int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a) {
                "durf_mlp_fwd(bf16): activation saving needs a topology with a tensor-core backward");
   TcParams P;
   build_sched(t, P, (t.width == 256 && a.saved == nullptr) ? 4 : 2);      // = TcCfg<W, SAVE>::SKB
-  P.saved = (uint8_t*)a.saved;
+  // `saved` may be a buffer for more ray-levels than this call's (several levels, one backward): records first, then masks
+  const int total = a.saved_total_tiles > 0 ? a.saved_total_tiles : a.M, off = a.saved_total_tiles > 0 ? a.saved_tile_offset : 0;
+  DURF_REQUIRE(off >= 0 && off + a.M <= total, DURF_E_INVALID, "durf_mlp_fwd(bf16): saved_tile_offset %d + M %d > saved_total_tiles %d",
+               off, a.M, total);
   P.saved_blocks_per_tile = mlp_tc_saved_blocks(t);
-  P.masks = P.saved ? reinterpret_cast<uint32_t*>(P.saved + (size_t)a.M * P.saved_blocks_per_tile * kBlockBytes) : nullptr;
+  P.saved = a.saved ? (uint8_t*)a.saved + (size_t)off * P.saved_blocks_per_tile * kBlockBytes : nullptr;
+  P.masks = a.saved ? reinterpret_cast<uint32_t*>((uint8_t*)a.saved + (size_t)total * P.saved_blocks_per_tile * kBlockBytes) +
+                          (size_t)off * (t.depth + 1) * (t.width / 32) * 128
+                    : nullptr;
   {
     MlpLayout L(t);
     P.off_bcond = (int)L.b_off[t.depth + 2];      // the per-tile view bias is formed inside the kernel (view_bias): no workspace

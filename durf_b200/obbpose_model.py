@@ -73,6 +73,12 @@ class MipNerfModel:
     # B200 it is not faster than running them back to back (both kernels are bound per SM, not by HBM, so
     # splitting the SMs between them only moves the time around): off by default.
     overlap_backward: bool = field(default_factory=lambda: os.environ.get('DURF_BWD_OVERLAP', '0') == '1')
+    # Batches of up to `shared_level_max_rays` rays: the levels of a training forward share one set of activation / mask / tile
+    # buffers, and the background network's backward is ONE data-gradient and ONE weight-gradient launch over all of them (the
+    # tail wave and the accumulator flush are paid once: -6.5 % at 512 rays, -1.7 % at 2,048; at 16,384 rays a pair of launches
+    # per level is 0.7 % faster - the weight-gradient kernel still finds part of its level's dZ in L2 - and is kept)
+    shared_level_backward: bool = field(default_factory=lambda: os.environ.get('DURF_SHARED_LEVELS', '1') != '0')
+    shared_level_max_rays: int = 4096
     overlap_min_rays: int = 2048
 
     # -- topology helpers ------------------------------------------------------------------------------
@@ -183,11 +189,26 @@ class MipNerfModel:
             else:
                 rm_kw.update(t_vals=t_vals)
             if fuse:
-                # training keeps the tile image in HBM as well: the weight-gradient kernel reads it (job 0 and the skip layer)
-                feat_bg = torch.empty(B, 128 * 64, device=dev, dtype=torch.bfloat16) if ctx is not None else None
+                # training keeps the tile image in HBM as well: the weight-gradient kernel reads it (job 0 and the skip layer).
+                # All levels write their tiles / activations / masks into ONE set of buffers (level i = tiles i*B .. (i+1)*B - 1),
+                # so that the background network's backward is one data-gradient and one weight-gradient launch for all levels
+                # (at the reference's 512-ray batch a launch is 3.5 waves: the tail wave and the accumulator flush are paid once).
+                shared = None
+                if (ctx is not None and self.shared_level_backward and B <= self.shared_level_max_rays
+                        and not (self.overlap_backward and B >= self.overlap_min_rays)):
+                    if i_level == 0:
+                        ctx['bg_shared'] = dict(saved=ops.mlp_saved_buffer(bt, self.num_levels * B, N, dev),
+                                                feat=torch.empty(self.num_levels * B, 128 * 64, device=dev, dtype=torch.bfloat16))
+                    shared = ctx['bg_shared']
+                if shared is not None:
+                    feat_bg = shared['feat'][i_level * B:(i_level + 1) * B]
+                else:
+                    feat_bg = torch.empty(B, 128 * 64, device=dev, dtype=torch.bfloat16) if ctx is not None else None
                 fz, t_vals, _keep = ops.fused_raymarch_args(origins_s, dirs_s, radii, N, **rm_kw)
                 raw_rgb, raw_density, saved_bg = ops.mlp_fwd(bt, feat_bg, viewenc, variables.blob('MLP_0'), M=B, N=N, precision=prec,
-                                                             packed=variables.packed.get('MLP_0'), save=ctx is not None, fused=fz)
+                                                             packed=variables.packed.get('MLP_0'), save=ctx is not None, fused=fz,
+                                                             saved_buf=None if shared is None else shared['saved'],
+                                                             saved_offset=i_level * B, saved_total=self.num_levels * B)
             else:
                 rm = ops.raymarch(origins_s, dirs_s, radii, N, bf16_tiles=bf16, **rm_kw)
                 t_vals, feat_bg = rm['t_vals'], rm['features']
@@ -255,11 +276,17 @@ class MipNerfModel:
         overlap = None
         if prec == L.PREC_BF16 and self.overlap_backward and B >= self.overlap_min_rays:
             overlap = ops.OverlappedBackward()
-        for lvl, g in zip(ctx['levels'], level_grads):
+        shared = ctx.get('bg_shared') if overlap is None else None      # all levels' records in one buffer: one backward call
+        nl = len(ctx['levels'])
+        if shared is not None:
+            g_rgb_all = torch.empty(nl, B, N, 3, device=d_flat.device)
+            g_den_all = torch.empty(nl, B, N, device=d_flat.device)
+        for i_lvl, (lvl, g) in enumerate(zip(ctx['levels'], level_grads)):
             g_rgb, g_den, g_dirs = ops.composite_bwd(lvl['raw_rgb'], lvl['raw_density'], lvl['t_vals'], fe['dirs_s'],
                                                      g['comp_rgb'], g['depth'], g['weights'], white_bkgd=ctx['white_bkgd'],
                                                      rand_bkgd=ctx['rand_bkgd'], density_bias=self.density_bias,
-                                                     want_d_dirs=pose_opt)
+                                                     want_d_dirs=pose_opt, out_rgb=None if shared is None else g_rgb_all[i_lvl],
+                                                     out_density=None if shared is None else g_den_all[i_lvl])
             raw_grads.append((g_rgb, g_den))
             if pose_opt:
                 d_ds += g_dirs * (fe['nhit'] > 0).float()[:, None]            # only object rays carry pose-dependent dirs
@@ -298,7 +325,13 @@ class MipNerfModel:
             for k, sk in enumerate(side):
                 with torch.cuda.stream(sk):
                     object_backward(k)
+        if shared is not None:
+            ops.mlp_bwd(bt, shared['feat'], viewenc.repeat(nl, 1), variables.blob('MLP_0'), shared['saved'],
+                        g_rgb_all.view(nl * B, N, 3), g_den_all.view(nl * B, N), variables.blob_of(d_flat, 'MLP_0'), M=nl * B, N=N,
+                        precision=prec, packed=variables.packed.get('MLP_0'))
         for lvl, (g_rgb, g_den) in zip(ctx['levels'], raw_grads):
+            if shared is not None:
+                break
             if overlap is not None:
                 overlap(bt, lvl['feat_bg'], viewenc, variables.blob('MLP_0'), lvl['saved_bg'], g_rgb, g_den,
                         variables.blob_of(d_flat, 'MLP_0'), M=B, N=N, packed=variables.packed.get('MLP_0'))

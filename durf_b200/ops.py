@@ -208,12 +208,13 @@ def mlp_pack(topo, blob: torch.Tensor, packed: Optional[torch.Tensor] = None) ->
 
 
 def _mlp_args(topo, precision, M, N, features, cond, blob, packed, ray_index, count, accumulate, raw_rgb, raw_density, saved,
-              workspace, fused=None):
+              workspace, fused=None, saved_offset=0, saved_total=0):
     return L.MlpArgs(topo=topology(topo), precision=precision, M=M, N=N, features=ptr(features), cond=ptr(cond),
                      params=ptr(blob), packed=ptr(packed), ray_index=ptr(ray_index), count=ptr(count),
                      accumulate=int(accumulate), raw_rgb=ptr(raw_rgb), raw_density=ptr(raw_density), saved=ptr(saved),
                      workspace=ptr(workspace), workspace_bytes=0 if workspace is None else workspace.numel() * workspace.element_size(),
-                     fused_raymarch=None if fused is None else C.addressof(fused))
+                     fused_raymarch=None if fused is None else C.addressof(fused), saved_tile_offset=int(saved_offset),
+                     saved_total_tiles=int(saved_total))
 
 
 def fused_raymarch_args(origins, dirs, radii, N: int, *, t_vals=None, near=None, far=None, t_rand=None, contract=False,
@@ -250,9 +251,12 @@ def fused_raymarch_args(origins, dirs, radii, N: int, *, t_vals=None, near=None,
 
 
 def mlp_fwd(topo, features, cond, blob, *, M: int, N: int, precision=L.PREC_BF16, packed=None, ray_index=None, count=None,
-            accumulate=False, raw_rgb=None, raw_density=None, num_rays_out=None, save=False, fused=None):
+            accumulate=False, raw_rgb=None, raw_density=None, num_rays_out=None, save=False, fused=None, saved_buf=None,
+            saved_offset=0, saved_total=0):
     """Returns (raw_rgb[B,N,3], raw_density[B,N], saved-or-None).  `fused` = the struct of `fused_raymarch_args`: the kernel
-    generates its input tiles itself (`features` may be None, or a tile buffer the generated tiles are also stored to)."""
+    generates its input tiles itself (`features` may be None, or a tile buffer the generated tiles are also stored to).
+    `saved_buf` / `saved_offset` / `saved_total` (tensor-core training): write this call's records into a buffer shared by
+    several calls (`mlp_saved_buffer`), so that ONE backward call covers them all."""
     t = topology(topo)
     dev = _dev(features if features is not None else cond)
     Bout = num_rays_out if num_rays_out is not None else M
@@ -269,9 +273,9 @@ def mlp_fwd(topo, features, cond, blob, *, M: int, N: int, precision=L.PREC_BF16
     else:
         ws = torch.empty(max(int(lib.durf_mlp_workspace_bytes(C.byref(t), precision, M, N, 0)) // 4, 1), device=dev)
         if save:      # training on the tensor-core path: every layer's bf16 activations as tile images
-            saved = torch.empty(max(int(lib.durf_mlp_saved_bytes(C.byref(t), precision, M, N)), 16), device=dev, dtype=torch.uint8)
+            saved = saved_buf if saved_buf is not None else mlp_saved_buffer(t, M, N, dev)
     a = _mlp_args(t, precision, M, N, features, f32(cond), f32(blob), packed, ray_index, count, accumulate, raw_rgb, raw_density,
-                  saved, ws, fused)
+                  saved, ws, fused, saved_offset=saved_offset, saved_total=saved_total if saved_buf is not None else 0)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -280,6 +284,12 @@ def mlp_fwd(topo, features, cond, blob, *, M: int, N: int, precision=L.PREC_BF16
         e1.record()
         PROFILE['mlp'].append((e0, e1))
     return raw_rgb, raw_density, saved
+
+
+def mlp_saved_buffer(topo, M: int, N: int, dev) -> torch.Tensor:
+    """The buffer `durf_mlp_fwd` keeps a tensor-core training forward's activations and masks in, for M ray-levels."""
+    t = topology(topo)
+    return torch.empty(max(int(L.load().durf_mlp_saved_bytes(C.byref(t), L.PREC_BF16, M, N)), 16), device=dev, dtype=torch.uint8)
 
 
 def mlp_bwd(topo, features, cond, blob, saved, d_raw_rgb, d_raw_density, d_blob, *, M: int, N: int, ray_index=None,
@@ -393,13 +403,13 @@ def composite(raw_rgb, raw_density, t_vals, dirs, *, white_bkgd=False, rand_bkgd
 
 
 def composite_bwd(raw_rgb, raw_density, t_vals, dirs, d_comp_rgb, d_depth, d_weights, *, d_acc=None, white_bkgd=False,
-                  rand_bkgd=False, activated=False, density_bias=-1.0, want_d_dirs=False):
+                  rand_bkgd=False, activated=False, density_bias=-1.0, want_d_dirs=False, out_rgb=None, out_density=None):
     raw_rgb, raw_density, t_vals, dirs = f32(raw_rgb), f32(raw_density), f32(t_vals), f32(dirs)
     raw_density = raw_density.reshape(raw_density.shape[0], -1)
     B, N = raw_density.shape
     dev = _dev(raw_rgb)
-    g_rgb = torch.empty(B, N, 3, device=dev)
-    g_den = torch.empty(B, N, device=dev)
+    g_rgb = out_rgb if out_rgb is not None else torch.empty(B, N, 3, device=dev)
+    g_den = out_density if out_density is not None else torch.empty(B, N, device=dev)
     g_dirs = torch.empty(B, 3, device=dev) if want_d_dirs else None
     a = _comp_args(raw_rgb, raw_density, t_vals, dirs, white_bkgd, rand_bkgd, activated, density_bias, {})
     check(L.load().durf_composite_bwd(stream_ptr(), C.byref(a), ptr(f32(d_comp_rgb)), ptr(f32(d_depth)), ptr(d_acc),

@@ -202,6 +202,12 @@ typedef struct DurfMlpArgs {
                                B, N = 128, min_deg / max_deg (10 degrees) and the flags are taken from it; ray_index / count are this
                                struct's; t_vals is written when DURF_RM_SAMPLE.  `features` may then be NULL; if it is not, the
                                generated tiles are ALSO stored there (training: the weight-gradient kernel reads them). */
+  int32_t saved_tile_offset;  /* [opt] BF16 training: `saved` (and `features`, when the generated tiles are stored) are buffers for  */
+  int32_t saved_total_tiles;  /* saved_total_tiles >= M ray-levels and this call fills the records saved_tile_offset .. + M - 1, so
+                                 that several forward calls (the levels of obbpose_model.py:133-256) share ONE backward call with
+                                 M = saved_total_tiles (one data-gradient and one weight-gradient launch for all levels).
+                                 0 / 0 = the buffer is this call's alone.  `features` itself is NOT offset: pass the pointer of
+                                 the first tile this call writes. */
 } DurfMlpArgs;
 
 size_t durf_mlp_workspace_bytes(const DurfMlpTopology* topo, int32_t precision, int32_t M, int32_t N, int32_t training);

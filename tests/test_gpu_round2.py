@@ -187,8 +187,8 @@ def test_overlapped_backward_equals_the_serial_backward(B, monkeypatch):
     from durf_b200 import ops
     wcap = ops.OverlappedBackward().weight_ctas
 
-    def grad(overlap):
-        model = _model(precision='bf16', overlap_backward=overlap, overlap_min_rays=0)
+    def grad(overlap, shared=False):
+        model = _model(precision='bf16', overlap_backward=overlap, overlap_min_rays=0, shared_level_backward=shared)
         st = TrainState.create(H.cuda_variables(sc, model))
         _, stats = train_step(model, config, rng, st, mk(1), lr=1e-3, eps=3.0, alpha=10.0)
         torch.cuda.synchronize()
@@ -203,6 +203,9 @@ def test_overlapped_backward_equals_the_serial_backward(B, monkeypatch):
     g_full, _ = grad(False)                        # all SMs: a different partition, fp32 summation-order noise only
     g_over, l_over = grad(True)
     assert float((g_serial - g_full).norm() / g_serial.norm()) <= 2e-4
+    # the default path: both levels in one data-gradient and one weight-gradient launch (again another partition of the sums)
+    g_shared, l_shared = grad(False, shared=True)
+    assert float((g_serial - g_shared).norm() / g_serial.norm()) <= 2e-4 and torch.equal(l_serial, l_shared)
     noise = float((g_serial - g_serial2).norm() / g_serial.norm())
     rel = float((g_serial - g_over).norm() / g_serial.norm())
     assert float(g_serial.norm()) > 0 and torch.isfinite(g_over).all()
