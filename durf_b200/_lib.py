@@ -28,6 +28,7 @@ RM_WEIGHTED = 1 << 3
 RM_CYLINDER = 1 << 4
 RM_NO_INTEGRATE = 1 << 5
 RM_OUT_BF16_TILE = 1 << 6
+RM_NO_TVALS_OUT = 1 << 7
 
 LP_STRIDE = 8
 LP_NAMES = ("rgb", "depth", "near", "empty", "sky", "distr")
@@ -114,6 +115,7 @@ SIGNATURES = {
     "durf_ray_box_intersection_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "durf_obb_frontend_bwd": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "durf_compact_hits": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "durf_mlp_merge_raw": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "durf_raymarch_fwd": (C.c_int, [_vp, C.POINTER(RaymarchArgs)]),
     "durf_raymarch_bwd": (C.c_int, [_vp, C.POINTER(RaymarchArgs), _vp, _vp, _vp]),
     "durf_viewdir_enc_fwd": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),

@@ -106,6 +106,7 @@ static int check_mlp(const DurfMlpArgs* a, const char* who) {
                "%s: null buffer", who);
   DURF_REQUIRE(a->precision == DURF_PREC_FP32 || a->precision == DURF_PREC_BF16, DURF_E_INVALID, "%s: unknown precision %d",
                who, a->precision);
+  DURF_REQUIRE(a->accumulate >= 0 && a->accumulate <= 2, DURF_E_INVALID, "%s: accumulate must be 0, 1 or 2 (got %d)", who, a->accumulate);
   return DURF_OK;
 }
 

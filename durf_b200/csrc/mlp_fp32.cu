@@ -274,14 +274,15 @@ int mlp_fp32_forward(cudaStream_t st, const DurfMlpArgs& a) {
     if (i % t.skip == 0 && i > 0) { in.a2 = x; in.lda2 = t.in_dim; in.k2 = t.in_dim; in.a2_div = 1; }
   }
   const int iD = t.depth, iB = t.depth + 1, iC = t.depth + 2, iR = t.depth + 3;
+  const int32_t* out_index = a.accumulate == 2 ? nullptr : a.ray_index;      // 2: compact output rows (durf_mlp_merge_raw)
   head_fwd_kernel<1><<<ceil_div(R, 8), 256, 0, st>>>((int)R, a.N, in, a.params + L.w_off[iD], a.params + L.b_off[iD],
-                                                      a.ray_index, a.accumulate, a.raw_density);
+                                                      out_index, a.accumulate == 1, a.raw_density);
   count_launch();
   launch_nn(st, false, (int)R, t.width, in, a.params + L.w_off[iB], t.width, a.params + L.b_off[iB], bott, t.width);
   RowSrc cin = RowSrc{bott, t.width, t.width, a.cond, t.cond_dim, t.cond_dim, a.N, a.ray_index};
   launch_nn(st, true, (int)R, t.cond_width, cin, a.params + L.w_off[iC], t.cond_width, a.params + L.b_off[iC], cond, t.cond_width);
   head_fwd_kernel<3><<<ceil_div(R, 8), 256, 0, st>>>((int)R, a.N, plain(cond, t.cond_width, t.cond_width), a.params + L.w_off[iR],
-                                                      a.params + L.b_off[iR], a.ray_index, a.accumulate, a.raw_rgb);
+                                                      a.params + L.b_off[iR], out_index, a.accumulate == 1, a.raw_rgb);
   count_launch();
   cudaError_t e = cudaGetLastError();
   DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_mlp_fwd(fp32): %s", cudaGetErrorString(e));

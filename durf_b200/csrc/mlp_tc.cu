@@ -491,7 +491,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
             const int r = gt + 64 * k;
             tf[k][0] = sample_fencepost(nr, fr, r, kTileM, tr_row);
             tf[k][1] = sample_fencepost(nr, fr, r + 1, kTileM, tr_row);
-            if (valid) {
+            if (valid && !(p.rm_flags & DURF_RM_NO_TVALS_OUT)) {
               p.g_t_vals[(size_t)ray * (kTileM + 1) + r] = tf[k][0];
               if (r == kTileM - 1) p.g_t_vals[(size_t)ray * (kTileM + 1) + kTileM] = tf[k][1];
             }
@@ -551,14 +551,14 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     // Per-tile housekeeping (raw outputs of the PREVIOUS tile, view bias of this one) is deferred until after layer 0's
     // epilogues, when the tensor core has a whole layer of MMAs queued: the tile boundary costs the issuer nothing.
     float den_prev = 0.f, rgb_prev[3] = {0.f, 0.f, 0.f};
-    int ray_prev = -1;
+    int ray_prev = -1, tile_prev = 0;
     auto flush_prev = [&]() {      // ch == 0 threads: combine the two column slices of every row, write raw outputs
-      const size_t o = (size_t)ray_prev * kTileM + row;
+      const size_t o = (size_t)(p.accumulate == 2 ? tile_prev : ray_prev) * kTileM + row;   // 2: compact rows (durf_mlp_merge_raw)
       const float dv = den_prev + s_part[row] + s_hb[0];
       const float r0 = rgb_prev[0] + s_part[128 + row] + s_hb[1];
       const float r1 = rgb_prev[1] + s_part[256 + row] + s_hb[2];
       const float r2 = rgb_prev[2] + s_part[384 + row] + s_hb[3];
-      if (p.accumulate) {
+      if (p.accumulate == 1) {
         p.raw_density[o] += dv;
         p.raw_rgb[o * 3 + 0] += r0; p.raw_rgb[o * 3 + 1] += r1; p.raw_rgb[o * 3 + 2] += r2;
       } else {
@@ -751,7 +751,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       } else {
         den_prev = den; rgb_prev[0] = rgb[0]; rgb_prev[1] = rgb[1]; rgb_prev[2] = rgb[2];
       }
-      ray_prev = ray;
+      ray_prev = ray; tile_prev = tile;
     }
     if (ray_prev >= 0) {             // the last tile's outputs
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -916,7 +916,9 @@ int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a) {
     const bool weighted = (rm->flags & DURF_RM_WEIGHTED) != 0;
     DURF_REQUIRE(rm->N == kTileM && rm->max_deg - rm->min_deg == 10 && t.in_dim == 60 + (weighted ? 3 : 0), DURF_E_UNSUPPORTED,
                  "durf_mlp_fwd(bf16): fused ray-march needs N = 128, 10 degrees and in_dim = 60 (IPE) / 63 (weighted IPE)");
-    DURF_REQUIRE(rm->origins && rm->dirs && rm->radii && rm->t_vals, DURF_E_INVALID, "durf_mlp_fwd(bf16): fused ray-march: null ray buffer");
+    DURF_REQUIRE(rm->origins && rm->dirs && rm->radii, DURF_E_INVALID, "durf_mlp_fwd(bf16): fused ray-march: null ray buffer");
+    DURF_REQUIRE(rm->t_vals || (rm->flags & (DURF_RM_SAMPLE | DURF_RM_NO_TVALS_OUT)) == (DURF_RM_SAMPLE | DURF_RM_NO_TVALS_OUT), DURF_E_INVALID,
+                 "durf_mlp_fwd(bf16): fused ray-march: t_vals missing");
     DURF_REQUIRE(!(rm->flags & DURF_RM_SAMPLE) || (rm->near && rm->far), DURF_E_INVALID, "durf_mlp_fwd(bf16): fused ray-march: near/far missing");
     DURF_REQUIRE(!(rm->flags & DURF_RM_RANDOMIZED) || rm->t_rand, DURF_E_INVALID, "durf_mlp_fwd(bf16): fused ray-march: t_rand missing");
   }

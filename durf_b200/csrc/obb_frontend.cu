@@ -3,6 +3,7 @@
 // 59-106) and the merge at obbpose_model.py:99-131.  One thread per ray, K rotations staged in shared memory.
 // HBM-bound: 24 B in, 28 + 12K B out per ray.
 #include "common.cuh"
+#include <algorithm>
 
 namespace durf {
 
@@ -363,5 +364,34 @@ extern "C" int durf_compact_hits(durf_stream_t stream, int32_t B, int32_t K, int
   if (B == 0) return DURF_OK;
   compact_hits_kernel<<<ceil_div(B, 256), 256, 0, (cudaStream_t)stream>>>(B, K, k, hit, ray_index, count);
   DURF_CHECK_LAUNCH("durf_compact_hits");
+  return DURF_OK;
+}
+
+// raw[ray_index[m]] += src[m]: the scatter half of an object network evaluated into compact rows (DurfMlpArgs.accumulate == 2).
+// One thread per sample; the rows of one ray are contiguous, so a warp moves 128 B of density and 384 B of colour per step.
+__global__ void __launch_bounds__(256)
+merge_raw_kernel(int M, int N, const int32_t* __restrict__ ray_index, const int32_t* __restrict__ count,
+                 const float* __restrict__ src_rgb, const float* __restrict__ src_density, float* __restrict__ raw_rgb,
+                 float* __restrict__ raw_density) {
+  const int rows = count ? min(*count, M) : M;
+  const int64_t total = (int64_t)rows * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N);
+    const int64_t o = (int64_t)ray_index[m] * N + (i - (int64_t)m * N);
+    raw_density[o] += src_density[i];
+    raw_rgb[3 * o + 0] += src_rgb[3 * i + 0];
+    raw_rgb[3 * o + 1] += src_rgb[3 * i + 1];
+    raw_rgb[3 * o + 2] += src_rgb[3 * i + 2];
+  }
+}
+
+extern "C" int durf_mlp_merge_raw(durf_stream_t stream, int32_t M, int32_t N, const int32_t* ray_index, const int32_t* count,
+                                  const float* src_rgb, const float* src_density, float* raw_rgb, float* raw_density) {
+  DURF_REQUIRE(M >= 0 && N >= 1, DURF_E_INVALID, "durf_mlp_merge_raw: bad shape M=%d N=%d", M, N);
+  if (M == 0) return DURF_OK;
+  DURF_REQUIRE(ray_index && src_rgb && src_density && raw_rgb && raw_density, DURF_E_INVALID, "durf_mlp_merge_raw: null argument");
+  const int blocks = (int)std::min<int64_t>(((int64_t)M * N + 255) / 256, 148 * 8);
+  merge_raw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(M, N, ray_index, count, src_rgb, src_density, raw_rgb, raw_density);
+  DURF_CHECK_LAUNCH("durf_mlp_merge_raw");
   return DURF_OK;
 }

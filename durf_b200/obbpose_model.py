@@ -78,6 +78,13 @@ class MipNerfModel:
     # tail wave and the accumulator flush are paid once: -6.5 % at 512 rays, -1.7 % at 2,048; at 16,384 rays a pair of launches
     # per level is 0.7 % faster - the weight-gradient kernel still finds part of its level's dZ in L2 - and is kept)
     shared_level_backward: bool = field(default_factory=lambda: os.environ.get('DURF_SHARED_LEVELS', '1') != '0')
+    # Batches of up to `concurrent_objects_max_rays` rays on the fused tensor-core path: every object network's forward runs on
+    # its own side stream NEXT TO the background network's instead of after it.  It writes compact rows (DurfMlpArgs.accumulate
+    # == 2; at level 0 it re-forms the fenceposts itself, DURF_RM_NO_TVALS_OUT) that durf_mlp_merge_raw adds into the per-ray
+    # outputs in object order afterwards - the sums of the serial path bit for bit.  At the reference's 512-ray batch the
+    # background network is 3.5 waves of tiles: the objects' tiles run on the SMs its last wave leaves idle.
+    concurrent_objects: bool = field(default_factory=lambda: os.environ.get('DURF_OBJ_CONCURRENT', '1') != '0')
+    concurrent_objects_max_rays: int = 4096
     shared_level_max_rays: int = 4096
     overlap_min_rays: int = 2048
 
@@ -188,6 +195,34 @@ class MipNerfModel:
                 rm_kw.update(near=rays.near, far=rays.far, t_rand=rb['t_rand'])
             else:
                 rm_kw.update(t_vals=t_vals)
+            # object networks next to the background network (see `concurrent_objects`)
+            conc = (fuse and self.dynamics and obj_prec == L.PREC_BF16 and self.concurrent_objects and K > 0
+                    and B <= self.concurrent_objects_max_rays)
+            pending = []
+            if conc:
+                cur = torch.cuda.current_stream()
+                side = _object_streams(dev, K)
+                o_kw = dict(weighted=True, alpha=alpha, min_deg=self.min_deg_point, max_deg=self.max_deg_point,
+                            ray_shape=self.ray_shape, integrate=not self.disable_integration)
+                if i_level == 0:
+                    o_kw.update(near=rays.near, far=rays.far, t_rand=rb['t_rand'], store_t_vals=False)
+                else:
+                    o_kw.update(t_vals=t_vals)
+                for k, (idx, cnt, _m) in enumerate(obj_lists):
+                    rows = B if self.max_obj_rays is None else min(B, self.max_obj_rays)
+                    # every buffer is allocated on the calling stream (the side stream only runs the kernel)
+                    feat_o = torch.empty(rows, 128 * 64, device=dev, dtype=torch.bfloat16) if ctx is not None else None
+                    saved_o = ops.mlp_saved_buffer(ot, rows, N, dev) if ctx is not None else None
+                    c_rgb, c_den = torch.empty(rows, N, 3, device=dev), torch.empty(rows, N, device=dev)
+                    fzo, _, _keep_o = ops.fused_raymarch_args(origins_s, dirs_s, radii, N, **o_kw)
+                    side[k].wait_stream(cur)
+                    with torch.cuda.stream(side[k]):
+                        ops.mlp_fwd(ot, feat_o, viewenc, variables.blob(f'BoxMLP_{k}'), M=rows, N=N, precision=obj_prec,
+                                    packed=variables.packed.get(f'BoxMLP_{k}'), ray_index=idx, count=cnt, accumulate=2,
+                                    raw_rgb=c_rgb, raw_density=c_den, save=ctx is not None, fused=fzo, saved_buf=saved_o,
+                                    saved_total=rows)
+                    pending.append(dict(feat=feat_o, saved=saved_o, rows=rows, count=cnt, c_rgb=c_rgb, c_den=c_den, idx=idx,
+                                        keep=_keep_o))
             if fuse:
                 # training keeps the tile image in HBM as well: the weight-gradient kernel reads it (job 0 and the skip layer).
                 # All levels write their tiles / activations / masks into ONE set of buffers (level i = tiles i*B .. (i+1)*B - 1),
@@ -216,7 +251,13 @@ class MipNerfModel:
                                                              precision=prec, packed=variables.packed.get('MLP_0'),
                                                              save=ctx is not None)
             lvl_ctx = dict(feat_bg=feat_bg, saved_bg=saved_bg, obj=[]) if ctx is not None else None
-            if self.dynamics:
+            if conc:
+                for k, o in enumerate(pending):
+                    cur.wait_stream(side[k])
+                    ops.mlp_merge_raw(o['c_rgb'], o['c_den'], o['idx'], o['count'], raw_rgb, raw_density)
+                    if lvl_ctx is not None:
+                        lvl_ctx['obj'].append(dict(feat=o['feat'], saved=o['saved'], rows=o['rows'], count=o['count']))
+            elif self.dynamics:
                 for k, (idx, cnt, m_host) in enumerate(obj_lists):
                     if m_host == 0:
                         if lvl_ctx is not None:

@@ -105,6 +105,13 @@ def compact_hits(hit: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]
     return idx, cnt
 
 
+def mlp_merge_raw(src_rgb, src_density, ray_index, count, raw_rgb, raw_density) -> None:
+    """raw[ray_index[m]] += src[m] for the rows of an object network evaluated with `mlp_fwd(..., accumulate=2)`."""
+    M, N = src_density.shape
+    check(L.load().durf_mlp_merge_raw(stream_ptr(), M, N, ptr(ray_index), ptr(count), ptr(src_rgb), ptr(src_density),
+                                      ptr(raw_rgb), ptr(raw_density)), "durf_mlp_merge_raw")
+
+
 # ---- K1 ---------------------------------------------------------------------------------------------
 def raymarch(origins, dirs, radii, N: int, *, t_vals=None, near=None, far=None, t_rand=None, contract=False,
              weighted=False, alpha=0.0, min_deg=0, max_deg=10, ray_shape='cone', integrate=True, ray_mult=None,
@@ -218,9 +225,12 @@ def _mlp_args(topo, precision, M, N, features, cond, blob, packed, ray_index, co
 
 
 def fused_raymarch_args(origins, dirs, radii, N: int, *, t_vals=None, near=None, far=None, t_rand=None, contract=False,
-                        weighted=False, alpha=0.0, min_deg=0, max_deg=10, ray_shape='cone', integrate=True, ray_mult=None):
+                        weighted=False, alpha=0.0, min_deg=0, max_deg=10, ray_shape='cone', integrate=True, ray_mult=None,
+                        store_t_vals=True):
     """The arguments of `raymarch` as a struct for `mlp_fwd(..., fused=...)` (the tcgen05 MLP kernel generates its
-    own input tiles).  Returns (struct, t_vals, keepalive): t_vals is allocated here when it is to be sampled."""
+    own input tiles).  Returns (struct, t_vals, keepalive): t_vals is allocated here when it is to be sampled.
+    `store_t_vals=False` (sampling only): the fenceposts are formed in registers and not written (t_vals is None) -- an
+    object network that runs next to the background network, whose call stores them."""
     if ray_shape not in ('cone', 'cylinder'):
         raise AssertionError("ray_shape must be 'cone' or 'cylinder'")
     origins, dirs = f32(origins), f32(dirs)
@@ -229,7 +239,10 @@ def fused_raymarch_args(origins, dirs, radii, N: int, *, t_vals=None, near=None,
     flags = 0
     if t_vals is None:
         flags |= L.RM_SAMPLE
-        t_vals = torch.empty(B, N + 1, device=_dev(origins))
+        if store_t_vals:
+            t_vals = torch.empty(B, N + 1, device=_dev(origins))
+        else:
+            flags |= L.RM_NO_TVALS_OUT
         near, far = f32(near).reshape(-1), f32(far).reshape(-1)
         if t_rand is not None:
             flags |= L.RM_RANDOMIZED

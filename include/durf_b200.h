@@ -101,6 +101,12 @@ int durf_obb_frontend_bwd(durf_stream_t stream, int32_t B, int32_t K,
                           const int32_t* hit, const float* d_origins_s, const float* d_dirs_s,
                           int32_t pose_grad, int32_t rot_grad, float* d_box);
 
+/* raw_rgb[ray_index[m]] += src_rgb[m], raw_density[ray_index[m]] += src_density[m] for m < *count (M when count is NULL):
+ * the second half of `raw += mask_k * BoxMLP_k(...)` (obbpose_model.py:203-204, 233-234) for a network evaluated with
+ * DurfMlpArgs.accumulate == 2.  Merging the objects in index order gives the sums of accumulate == 1 bit for bit. */
+int durf_mlp_merge_raw(durf_stream_t stream, int32_t M, int32_t N, const int32_t* ray_index, const int32_t* count,
+                       const float* src_rgb, const float* src_density, float* raw_rgb, float* raw_density);
+
 /* Compaction of the rays that hit object k (the reference evaluates every BoxMLP on every ray and
  * multiplies by the 0/1 mask, obbpose_model.py:174-201; evaluating only hit rays is result-identical).
  * ray_index [B] receives the indices (in NO particular order: warp-aggregated atomics; every consumer scatters its
@@ -132,6 +138,8 @@ int durf_generate_rays(durf_stream_t stream, const DurfCamera* cam, int32_t row0
 #define DURF_RM_CYLINDER      (1u << 4)  /* ray_shape == 'cylinder' (mip.py:133-152) */
 #define DURF_RM_NO_INTEGRATE  (1u << 5)  /* disable_integration: zero covariances (obbpose_model.py:164-165) */
 #define DURF_RM_OUT_BF16_TILE (1u << 6)  /* features as bf16 128x64 SWIZZLE_128B tile images (input of the tcgen05 MLP) */
+#define DURF_RM_NO_TVALS_OUT  (1u << 7)  /* fused_raymarch only, with DURF_RM_SAMPLE: the fenceposts are formed but not stored (t_vals may
+                                            be NULL): an object network evaluated next to the background network, which stores them */
 
 typedef struct DurfRaymarchArgs {
   int32_t B;            /* rays in the buffers */
@@ -185,7 +193,9 @@ typedef struct DurfMlpArgs {
   const void* packed;       /* tensor-core weight image (BF16) */
   const int32_t* ray_index; /* [opt] [M] output rows go to ray ray_index[m] */
   const int32_t* count;     /* [opt] device count of valid rays */
-  int32_t accumulate;       /* 0: write, 1: add into raw_rgb/raw_density (object MLPs, obbpose_model.py:203-204,233-234) */
+  int32_t accumulate;       /* 0: write, 1: add into raw_rgb/raw_density (object MLPs, obbpose_model.py:203-204,233-234),
+                               2: write row m of the call (NOT ray ray_index[m]): compact outputs [M,N,3] / [M,N] that
+                               durf_mlp_merge_raw adds into the per-ray buffers later, so that the call does not depend on them */
   float* raw_rgb;           /* [B,N,3] */
   float* raw_density;       /* [B,N] */
   void* saved;              /* [opt] kept for the backward pass (durf_mlp_saved_bytes): FP32 the layer outputs; BF16 every

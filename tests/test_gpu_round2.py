@@ -250,6 +250,50 @@ def test_fused_raymarch_is_the_separate_raymarch(randomized):
         assert torch.equal(x.view(torch.int16), y.view(torch.int16)), "stored feature tiles differ"
 
 
+@pytest.mark.parametrize("randomized", [False, True])
+def test_concurrent_object_networks_are_the_serial_ones(randomized):
+    """`concurrent_objects`: the object networks' forward runs on side streams next to the background network, into compact
+    rows (DurfMlpArgs.accumulate == 2, fenceposts re-formed in the kernel at level 0: DURF_RM_NO_TVALS_OUT) that
+    durf_mlp_merge_raw adds in object order.  raw = MLP_0 + mask_0 * BoxMLP_0 + mask_1 * BoxMLP_1 in the reference's order
+    (obbpose_model.py:203-204, 233-234), so model outputs, stored tiles and the gradient of a whole train step must be
+    IDENTICAL to the serial accumulate == 1 path."""
+    from durf_b200.train import TrainState, train_step
+    from durf_b200.utils import Config
+    sc = H.scene(B=700, K=2, seed=47)
+    outs = {}
+    for conc in (True, False):
+        model = _model(precision='bf16', concurrent_objects=conc)
+        v = H.cuda_variables(sc, model)
+        rng = dict(t_rand=cu(sc['t_rand']), u_rand=cu(sc['u_rand'])) if randomized else None
+        for training in (False, True):
+            ctx = {} if training else None
+            ret = model.apply(v, rng, H.cuda_rays(sc), None, cu(sc['ext']), torch.tensor([1]), randomized, False, False, 4.5, ctx=ctx)
+            torch.cuda.synchronize()
+            outs[(conc, training)] = [tuple(lv[i].clone() for i in range(5)) for lv in ret]
+            if training:
+                outs[(conc, 'feat')] = [o['feat'].clone() for lvl in ctx['levels'] for o in lvl['obj']]
+    for training in (False, True):
+        for a, b in zip(outs[(True, training)], outs[(False, training)]):
+            for x, y, name in zip(a, b, ('comp_rgb', 'depth', 'acc', 'weights', 't_vals')):
+                assert torch.equal(x, y), f"{name} differs (training={training}): max |d| = {float((x - y).abs().max()):.3e}"
+    assert len(outs[(True, 'feat')]) == 4
+    # compacted indices are unordered (warp-aggregated atomics): compare the object tiles as sets of rows per ray elsewhere;
+    # here the whole step's gradient, which every stored record feeds
+    sc2, mk, rng2 = _train_inputs(1024, 2, seed=95)
+    grads = []
+    for conc in (True, False):
+        model = _model(precision='bf16', concurrent_objects=conc)
+        st = TrainState.create(H.cuda_variables(sc2, model))
+        _, stats = train_step(model, Config(), rng2, st, mk(1), lr=1e-3, eps=3.0, alpha=10.0)
+        torch.cuda.synchronize()
+        grads.append((stats['grad'].clone(), stats['loss'].clone()))
+    assert torch.equal(grads[0][1], grads[1][1]), "loss differs"
+    d = (grads[0][0] - grads[1][0]).abs().max()
+    # the object networks' weight gradients sum their tiles in the order of the (unordered) compaction: equal up to fp32
+    # summation order, and exactly equal for the background network
+    assert float(d) <= 1e-6 * float(grads[1][0].abs().max()) + 1e-9, float(d)
+
+
 def test_loss_value_is_bit_reproducible_and_step_has_no_host_sync():
     """The loss reduction is deterministic (fixed-order block partials instead of float atomics), and a bf16 train step issues
     no device->host read (checked with torch's sync debug mode)."""
