@@ -29,6 +29,7 @@ RM_CYLINDER = 1 << 4
 RM_NO_INTEGRATE = 1 << 5
 RM_OUT_BF16_TILE = 1 << 6
 RM_NO_TVALS_OUT = 1 << 7
+RM_MULT_IS_NHIT = 1 << 8
 
 LP_STRIDE = 8
 LP_NAMES = ("rgb", "depth", "near", "empty", "sky", "distr")
@@ -115,12 +116,14 @@ SIGNATURES = {
     "durf_ray_box_intersection_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "durf_obb_frontend_bwd": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "durf_compact_hits": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "durf_compact_hits_all": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "durf_mlp_merge_raw": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "durf_raymarch_fwd": (C.c_int, [_vp, C.POINTER(RaymarchArgs)]),
     "durf_raymarch_bwd": (C.c_int, [_vp, C.POINTER(RaymarchArgs), _vp, _vp, _vp]),
     "durf_viewdir_enc_fwd": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "durf_mlp_packed_bytes": (_i64, [C.POINTER(MlpTopology)]),
     "durf_mlp_pack_weights": (C.c_int, [_vp, C.POINTER(MlpTopology), _vp, _vp]),
+    "durf_mlp_pack_weights_multi": (C.c_int, [_vp, _i32, C.POINTER(MlpTopology), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "durf_mlp_workspace_bytes": (C.c_size_t, [C.POINTER(MlpTopology), _i32, _i32, _i32, _i32]),
     "durf_mlp_saved_bytes": (C.c_size_t, [C.POINTER(MlpTopology), _i32, _i32, _i32]),
     "durf_mlp_fwd": (C.c_int, [_vp, C.POINTER(MlpArgs)]),

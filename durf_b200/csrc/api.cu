@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "mlp_topology.h"
 
@@ -26,13 +28,13 @@ int mlp_fp32_forward(cudaStream_t st, const DurfMlpArgs& a);
 int mlp_fp32_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density,
                       float* d_params, float* d_features);
 int64_t mlp_tc_packed_bytes(const DurfMlpTopology& t);
-int mlp_tc_pack(cudaStream_t st, const DurfMlpTopology& t, const float* params, void* packed);
+int mlp_tc_pack_blocks(const DurfMlpTopology& t, const float* params, void* packed, std::vector<PackBlock>& out);
 int mlp_tc_forward(cudaStream_t st, const DurfMlpArgs& a);
 size_t mlp_tc_workspace_bytes(const DurfMlpTopology& t, int64_t M);
 bool mlp_tc_bwd_supported(const DurfMlpTopology& t);
 int mlp_tc_saved_blocks(const DurfMlpTopology& t);
 int64_t mlp_tc_packed_t_bytes(const DurfMlpTopology& t);
-int mlp_tc_pack_t(cudaStream_t st, const DurfMlpTopology& t, const float* params, void* packed_t);
+int mlp_tc_pack_t_blocks(const DurfMlpTopology& t, const float* params, void* packed_t, std::vector<PackBlock>& out);
 int mlp_tc_backward(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density, float* d_params,
                     float* d_features);
 int mlp_tc_backward_data(cudaStream_t st, const DurfMlpArgs& a, const float* d_raw_rgb, const float* d_raw_density,
@@ -68,11 +70,23 @@ extern "C" int64_t durf_mlp_packed_bytes(const DurfMlpTopology* topo) {
   return mlp_tc_packed_bytes(*topo) + mlp_tc_packed_t_bytes(*topo);   // forward image, then the transposed image of dgrad
 }
 
+extern "C" int durf_mlp_pack_weights_multi(durf_stream_t stream, int32_t n, const DurfMlpTopology* topos, const float* const* params,
+                                           void* const* packed) {
+  DURF_REQUIRE(n >= 0 && (n == 0 || (topos && params && packed)), DURF_E_INVALID, "durf_mlp_pack_weights: bad argument");
+  std::vector<PackBlock> blocks;
+  for (int i = 0; i < n; ++i) {
+    DURF_REQUIRE(topology_ok(&topos[i]) && params[i] && packed[i], DURF_E_INVALID, "durf_mlp_pack_weights: bad argument (network %d)", i);
+    int rc = mlp_tc_pack_blocks(topos[i], params[i], packed[i], blocks);
+    if (rc < 0) return rc;
+    if (!mlp_tc_bwd_supported(topos[i])) continue;
+    rc = mlp_tc_pack_t_blocks(topos[i], params[i], (uint8_t*)packed[i] + mlp_tc_packed_bytes(topos[i]), blocks);
+    if (rc < 0) return rc;
+  }
+  return pack_blocks_launch((cudaStream_t)stream, blocks.data(), (int)blocks.size());
+}
+
 extern "C" int durf_mlp_pack_weights(durf_stream_t stream, const DurfMlpTopology* topo, const float* params, void* packed) {
-  DURF_REQUIRE(topology_ok(topo) && params && packed, DURF_E_INVALID, "durf_mlp_pack_weights: bad argument");
-  int rc = mlp_tc_pack((cudaStream_t)stream, *topo, params, packed);
-  if (rc != DURF_OK || !mlp_tc_bwd_supported(*topo)) return rc;
-  return mlp_tc_pack_t((cudaStream_t)stream, *topo, params, (uint8_t*)packed + mlp_tc_packed_bytes(*topo));
+  return durf_mlp_pack_weights_multi(stream, 1, topo, &params, &packed);
 }
 
 extern "C" size_t durf_mlp_workspace_bytes(const DurfMlpTopology* topo, int32_t precision, int32_t M, int32_t N, int32_t training) {

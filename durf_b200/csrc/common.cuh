@@ -38,6 +38,17 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 template <class... P>
 static inline bool aligned16(const P*... p) { return ((... | reinterpret_cast<uintptr_t>(p)) & 15u) == 0; }
 
+// ---- weight images of the tensor-core kernels (mlp_tc*.cu) ------------------------------------------
+// One 16 KB block of a weight image: block[r][k] = src[r * sr + k * sk] for r < r_avail, k < k_avail, else 0 (the forward image
+// takes rows = output columns of a kernel, the transposed image of the data-gradient kernel rows = input rows).
+struct PackBlock {
+  const float* src;
+  uint8_t* dst;
+  int32_t sr, sk, r_avail, k_avail;
+};
+constexpr int kPackMaxBlocks = 448;     // blocks per launch of pack_blocks_kernel (14 KB of kernel parameters)
+int pack_blocks_launch(cudaStream_t st, const PackBlock* blocks, int n);
+
 // ---- device helpers ---------------------------------------------------------------------------
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;

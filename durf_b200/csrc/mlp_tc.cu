@@ -26,6 +26,8 @@
 // 1-bit ReLU masks and the generated tile for the backward kernels (save_piece).
 #include <stdlib.h>
 
+#include <vector>
+
 #include "tc_common.cuh"
 #include "mlp_topology.h"
 #include "raymarch_device.cuh"
@@ -481,7 +483,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
         const float d[3] = {p.g_dirs[3 * ray], p.g_dirs[3 * ray + 1], p.g_dirs[3 * ray + 2]};
         const float radius = p.g_radii[ray];
         const bool has_mult = p.g_ray_mult != nullptr;
-        const float mult = has_mult ? p.g_ray_mult[ray] : 1.f;
+        const float mult = !has_mult ? 1.f : ((p.rm_flags & DURF_RM_MULT_IS_NHIT) ? 1.f - p.g_ray_mult[ray] : p.g_ray_mult[ray]);
         float tf[2][2];                                      // fenceposts (r, r+1) of this thread's rows gt and gt + 64
         if (sample) {
           const float nr = p.g_near[ray], fr = p.g_far[ray];
@@ -768,34 +770,39 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-// fp32 parameter blob -> bf16 weight image: for every GEMM layer, N half and K block (the order the kernel
-// consumes them) one 128 x 64 K-major SWIZZLE_128B block of 16 KB.  One thread per 16-byte piece.
-constexpr int kMaxBlocks = 192;
-struct PackParams {
-  const float* params;
-  uint8_t* packed;
+// fp32 parameter blob -> bf16 weight images: for every GEMM layer, N half and K block (the order the kernels consume them)
+// one 128 x 64 K-major SWIZZLE_128B block of 16 KB.  One thread per 16-byte piece; ONE launch covers the forward and the
+// transposed images of every network handed to durf_mlp_pack_weights_multi.
+struct PackMultiParams {
   int n_blocks;
-  // per block: source kernel offset, its leading dimension (= out dim), first source row, rows available, first column
-  int w_off[kMaxBlocks], ld[kMaxBlocks], k_first[kMaxBlocks], k_avail[kMaxBlocks], n_first[kMaxBlocks], n_avail[kMaxBlocks];
+  int pad;
+  PackBlock b[kPackMaxBlocks];
 };
-__global__ void pack_weights_kernel(const __grid_constant__ PackParams p) {
+__global__ void pack_blocks_kernel(const __grid_constant__ PackMultiParams p) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)p.n_blocks * 1024) return;
   const int blk = (int)(i / 1024), r = (int)(i % 1024) / 8, c = (int)(i % 8);
+  const PackBlock& B = p.b[blk];
+  const float* src = B.src + (size_t)r * B.sr;
+  const bool row_ok = r < B.r_avail;
   uint32_t w[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    float v[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int k = c * 8 + 2 * e + h;
-      v[h] = (k < p.k_avail[blk] && r < p.n_avail[blk])
-                 ? p.params[p.w_off[blk] + (size_t)(p.k_first[blk] + k) * p.ld[blk] + p.n_first[blk] + r]
-                 : 0.f;
-    }
-    w[e] = pack_bf16x2(v[0], v[1]);
+    const int k = c * 8 + 2 * e;
+    w[e] = pack_bf16x2(row_ok && k < B.k_avail ? src[(size_t)k * B.sk] : 0.f, row_ok && k + 1 < B.k_avail ? src[(size_t)(k + 1) * B.sk] : 0.f);
   }
-  *reinterpret_cast<uint4*>(p.packed + (size_t)blk * kBlockBytes + sw128_offset(r, c)) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(B.dst + sw128_offset(r, c)) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+int pack_blocks_launch(cudaStream_t st, const PackBlock* blocks, int n) {
+  for (int first = 0; first < n; first += kPackMaxBlocks) {
+    PackMultiParams pp;
+    pp.n_blocks = n - first < kPackMaxBlocks ? n - first : kPackMaxBlocks; pp.pad = 0;
+    for (int i = 0; i < pp.n_blocks; ++i) pp.b[i] = blocks[first + i];
+    pack_blocks_kernel<<<ceil_div((int64_t)pp.n_blocks * 1024, 256), 256, 0, st>>>(pp);
+    DURF_CHECK_LAUNCH("durf_mlp_pack_weights");
+  }
+  return DURF_OK;
 }
 
 static bool tc_supported(const DurfMlpTopology& t) {
@@ -872,32 +879,32 @@ int64_t mlp_tc_packed_bytes(const DurfMlpTopology& t) {
   return (int64_t)build_sched(t, P) * kBlockBytes;
 }
 
-int mlp_tc_pack(cudaStream_t st, const DurfMlpTopology& t, const float* params, void* packed) {
+// Appends the block descriptions of the forward image to `out`; returns their number (or a negative error code).
+int mlp_tc_pack_blocks(const DurfMlpTopology& t, const float* params, void* packed, std::vector<PackBlock>& out) {
   DURF_REQUIRE(tc_supported(t), DURF_E_UNSUPPORTED,
                "durf_mlp_pack_weights: tensor-core path needs width 128/256, cond_width 128, in_dim <= 64, depth <= 9");
   TcParams P;
   const int blocks = build_sched(t, P);
-  DURF_REQUIRE(blocks <= kMaxBlocks && P.n_steps <= kMaxSteps && P.n_uses <= kMaxStageUses, DURF_E_UNSUPPORTED,
+  DURF_REQUIRE(P.n_steps <= kMaxSteps && P.n_uses <= kMaxStageUses, DURF_E_UNSUPPORTED,
                "durf_mlp_pack_weights: too many weight blocks (%d)", blocks);
   MlpLayout L(t);
-  PackParams pp;
-  pp.params = params; pp.packed = (uint8_t*)packed; pp.n_blocks = blocks;
   for (int c = 0; c < P.n_steps; ++c) {          // block c of the image = K block of step c (same order as the ring-stage uses)
     const StepSched& sp = P.steps[c];
     const int g = sp.g;
     const int layer = (g < t.depth) ? g : (g == t.depth ? t.depth + 1 : t.depth + 2);
     const int n_out = L.out_dim[layer];
-    pp.w_off[c] = (int)L.w_off[layer];
-    pp.ld[c] = n_out;
-    pp.n_first[c] = sp.nh * 128;
-    pp.n_avail[c] = n_out - sp.nh * 128 < 128 ? n_out - sp.nh * 128 : 128;
-    if (!sp.inp) { pp.k_first[c] = sp.kb * 64; pp.k_avail[c] = 64; }
-    else { pp.k_first[c] = (g == 0) ? 0 : t.width; pp.k_avail[c] = t.in_dim; }   // input-feature block (skip rows follow the trunk rows)
+    const int n_first = sp.nh * 128;
+    // K rows of the block: a trunk K block, or the input features (for the skip layer they follow the trunk rows)
+    const int k_first = !sp.inp ? sp.kb * 64 : (g == 0 ? 0 : t.width);
+    PackBlock b;
+    b.src = params + L.w_off[layer] + (size_t)k_first * n_out + n_first;
+    b.dst = (uint8_t*)packed + (size_t)c * kBlockBytes;
+    b.sr = 1; b.sk = n_out;                      // block[r][k] = kernel[k_first + k][n_first + r]
+    b.r_avail = n_out - n_first < 128 ? n_out - n_first : 128;
+    b.k_avail = !sp.inp ? 64 : t.in_dim;
+    out.push_back(b);
   }
-  const int64_t total = (int64_t)blocks * 1024;
-  pack_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(pp);
-  DURF_CHECK_LAUNCH("durf_mlp_pack_weights");
-  return DURF_OK;
+  return blocks;
 }
 
 bool mlp_tc_bwd_supported(const DurfMlpTopology& t);

@@ -17,6 +17,8 @@
 // (its samples depend on no parameter).
 #include <stdlib.h>
 
+#include <vector>
+
 #include "tc_common.cuh"
 #include "mlp_topology.h"
 
@@ -488,30 +490,8 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
 
 // ---- host side -----------------------------------------------------------------------------------------------
 // Transposed weight image: for every backward stage, N half and K block one 128 x 64 block with
-// block[r][k] = kernel[in = n_first + r][out = k_first + k] (the contraction runs over the forward layer's outputs).
-constexpr int kDgMaxBlocks = 192;
-struct PackTParams {
-  const float* params;
-  uint8_t* packed;
-  int n_blocks;
-  int w_off[kDgMaxBlocks], ld[kDgMaxBlocks], in_first[kDgMaxBlocks], in_avail[kDgMaxBlocks], out_first[kDgMaxBlocks],
-      out_avail[kDgMaxBlocks];
-};
-__global__ void pack_weights_t_kernel(const __grid_constant__ PackTParams p) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)p.n_blocks * 1024) return;
-  const int blk = (int)(i / 1024), r = (int)(i % 1024) / 8, c = (int)(i % 8);
-  const float* src = p.params + p.w_off[blk] + (size_t)(p.in_first[blk] + r) * p.ld[blk] + p.out_first[blk] + c * 8;
-  uint32_t w[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int k = c * 8 + 2 * e;
-    const bool row_ok = r < p.in_avail[blk];
-    w[e] = pack_bf16x2(row_ok && k < p.out_avail[blk] ? src[2 * e] : 0.f, row_ok && k + 1 < p.out_avail[blk] ? src[2 * e + 1] : 0.f);
-  }
-  *reinterpret_cast<uint4*>(p.packed + (size_t)blk * kBlockBytes + sw128_offset(r, c)) = make_uint4(w[0], w[1], w[2], w[3]);
-}
-
+// block[r][k] = kernel[in = n_first + r][out = k_first + k] (the contraction runs over the forward layer's outputs); written
+// by pack_blocks_kernel (mlp_tc.cu) from the PackBlock list built here.
 bool mlp_tc_bwd_supported(const DurfMlpTopology& t) {
   return (t.width == 256 || t.width == 128) && t.cond_width == 128 && t.in_dim <= 64 && t.depth >= 2 && t.depth <= 9 &&
          t.cond_dim <= 32 && !(((t.depth - 1) % t.skip == 0) && t.depth - 1 > 0);
@@ -521,7 +501,8 @@ int mlp_tc_saved_blocks(const DurfMlpTopology& t) { return (t.depth + 1) * (t.wi
 
 // stage list + per-block source description; returns the number of blocks of the transposed image.  The image always
 // carries the input-gradient blocks (width 128 only); `want_dx` decides whether the kernel walks those last two entries.
-static int build_dg(const DurfMlpTopology& t, DgParams& P, PackTParams* pp, bool want_dx = false) {
+static int build_dg(const DurfMlpTopology& t, DgParams& P, std::vector<PackBlock>* pp, bool want_dx = false,
+                    const float* params = nullptr, uint8_t* packed_t = nullptr) {
   MlpLayout L(t);
   const int KB = t.width / 64, NH = t.width / 128;
   auto slot = [&](int g) { return g * KB; };
@@ -535,11 +516,14 @@ static int build_dg(const DurfMlpTopology& t, DgParams& P, PackTParams* pp, bool
     for (int nh = 0; nh < S.n_halves; ++nh)
       for (int kb = 0; kb < n_kb; ++kb, ++blocks)
         if (pp) {
-          pp->w_off[blocks] = (int)L.w_off[layer]; pp->ld[blocks] = L.out_dim[layer];
-          pp->in_first[blocks] = in_first + nh * 128;
-          pp->in_avail[blocks] = in_avail - nh * 128 < 128 ? (in_avail - nh * 128 < 0 ? 0 : in_avail - nh * 128) : 128;
-          pp->out_first[blocks] = kb * 64;
-          pp->out_avail[blocks] = L.out_dim[layer] - kb * 64 < 64 ? L.out_dim[layer] - kb * 64 : 64;
+          const int ld = L.out_dim[layer], row0 = in_first + nh * 128, left = in_avail - nh * 128;
+          PackBlock b;
+          b.src = params + L.w_off[layer] + (size_t)row0 * ld + kb * 64;
+          b.dst = packed_t + (size_t)blocks * kBlockBytes;
+          b.sr = ld; b.sk = 1;
+          b.r_avail = left < 128 ? (left < 0 ? 0 : left) : 128;
+          b.k_avail = ld - kb * 64 < 64 ? ld - kb * 64 : 64;
+          pp->push_back(b);
         }
     return S;
   };
@@ -582,16 +566,11 @@ int64_t mlp_tc_packed_t_bytes(const DurfMlpTopology& t) {
   return (int64_t)build_dg(t, P, nullptr) * kBlockBytes;
 }
 
-int mlp_tc_pack_t(cudaStream_t st, const DurfMlpTopology& t, const float* params, void* packed_t) {
+// Appends the block descriptions of the transposed image to `out`; returns their number (or a negative error code).
+int mlp_tc_pack_t_blocks(const DurfMlpTopology& t, const float* params, void* packed_t, std::vector<PackBlock>& out) {
   DURF_REQUIRE(mlp_tc_bwd_supported(t), DURF_E_UNSUPPORTED, "durf_mlp_pack_weights: no tensor-core backward for this topology");
   DgParams P;
-  PackTParams pp;
-  const int blocks = build_dg(t, P, &pp);
-  DURF_REQUIRE(blocks <= kDgMaxBlocks, DURF_E_UNSUPPORTED, "durf_mlp_pack_weights: too many transposed blocks (%d)", blocks);
-  pp.params = params; pp.packed = (uint8_t*)packed_t; pp.n_blocks = blocks;
-  pack_weights_t_kernel<<<ceil_div((int64_t)blocks * 1024, 256), 256, 0, st>>>(pp);
-  DURF_CHECK_LAUNCH("durf_mlp_pack_weights(transposed)");
-  return DURF_OK;
+  return build_dg(t, P, &out, false, params, (uint8_t*)packed_t);
 }
 
 int mlp_tc_dgrad_launch(cudaStream_t st, const DurfMlpTopology& t, const DgParams& base) {

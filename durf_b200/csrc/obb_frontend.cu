@@ -182,8 +182,14 @@ ray_box_kernel(int64_t n, const float* __restrict__ ray_o, const float* __restri
 }
 
 // Warp-aggregated compaction of the rays with hit[:,k] != 0 (unordered: results are scattered back per ray).
+// k < 0: one object per blockIdx.y, lists [K,B] and counts [K] (durf_compact_hits_all)
 __global__ void compact_hits_kernel(int B, int K, int k, const int32_t* __restrict__ hit,
                                     int32_t* __restrict__ ray_index, int32_t* __restrict__ count) {
+  if (k < 0) {
+    k = blockIdx.y;
+    ray_index += (size_t)k * B;
+    count += k;
+  }
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const bool h = (b < B) && hit[(size_t)b * K + k] != 0;
   const unsigned m = __ballot_sync(kFull, h);
@@ -364,6 +370,18 @@ extern "C" int durf_compact_hits(durf_stream_t stream, int32_t B, int32_t K, int
   if (B == 0) return DURF_OK;
   compact_hits_kernel<<<ceil_div(B, 256), 256, 0, (cudaStream_t)stream>>>(B, K, k, hit, ray_index, count);
   DURF_CHECK_LAUNCH("durf_compact_hits");
+  return DURF_OK;
+}
+
+extern "C" int durf_compact_hits_all(durf_stream_t stream, int32_t B, int32_t K, const int32_t* hit, int32_t* ray_index,
+                                     int32_t* count) {
+  DURF_REQUIRE(B >= 0 && K >= 1 && K <= kMaxObjects && count && (B == 0 || (hit && ray_index)), DURF_E_INVALID,
+               "durf_compact_hits_all: bad argument");
+  cudaError_t e = cudaMemsetAsync(count, 0, K * sizeof(int32_t), (cudaStream_t)stream);
+  DURF_REQUIRE(e == cudaSuccess, DURF_E_LAUNCH, "durf_compact_hits_all: memset: %s", cudaGetErrorString(e));
+  if (B == 0) return DURF_OK;
+  compact_hits_kernel<<<dim3(ceil_div(B, 256), K), 256, 0, (cudaStream_t)stream>>>(B, K, -1, hit, ray_index, count);
+  DURF_CHECK_LAUNCH("durf_compact_hits_all");
   return DURF_OK;
 }
 

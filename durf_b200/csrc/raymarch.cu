@@ -99,7 +99,7 @@ raymarch_fwd_kernel(const RayMarchParams p) {
     const float d[3] = {a.dirs[3 * ray], a.dirs[3 * ray + 1], a.dirs[3 * ray + 2]};
     const float radius = a.radii[ray];
     const bool has_mult = a.ray_mult != nullptr;
-    const float mult = has_mult ? a.ray_mult[ray] : 1.f;
+    const float mult = !has_mult ? 1.f : ((a.flags & DURF_RM_MULT_IS_NHIT) ? 1.f - a.ray_mult[ray] : a.ray_mult[ray]);
     const bool fast_tiles = (a.flags & DURF_RM_OUT_BF16_TILE) && p.D == 10;
     for (int n = lane; n < N; n += 32) {
       const Gauss g = sample_gaussian(a.flags, o, d, radius, mult, has_mult, s_t[n], s_t[n + 1]);
@@ -177,7 +177,7 @@ raymarch_bwd_kernel(const RayMarchParams p, const float* __restrict__ d_features
     const float o[3] = {a.origins[3 * ray], a.origins[3 * ray + 1], a.origins[3 * ray + 2]};
     const float d[3] = {a.dirs[3 * ray], a.dirs[3 * ray + 1], a.dirs[3 * ray + 2]};
     const float radius = a.radii[ray];
-    const float mult = a.ray_mult ? a.ray_mult[ray] : 1.f;
+    const float mult = !a.ray_mult ? 1.f : ((a.flags & DURF_RM_MULT_IS_NHIT) ? 1.f - a.ray_mult[ray] : a.ray_mult[ray]);
     float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
     for (int n = lane; n < N; n += 32) {
       const float t0 = s_t[n], t1 = s_t[n + 1];

@@ -161,11 +161,12 @@ class MipNerfModel:
         obj_lists = []
         bg_mult = None
         if self.dynamics:
-            bg_mult = 1.0 - fe['nhit']                                       # 1 - sum_k mask_k (obbpose_model.py:205)
+            bg_mult = fe['nhit']               # the kernels form 1 - sum_k mask_k (obbpose_model.py:205) from it: ray_mult_is_nhit
             cap = B if self.max_obj_rays is None else min(B, self.max_obj_rays)
             overflow = torch.zeros((), device=dev, dtype=torch.bool) if cap < B else None
+            idx_all, cnt_all = ops.compact_hits_all(hit)
             for k in range(K):
-                idx, cnt = ops.compact_hits(hit, k)
+                idx, cnt = idx_all[k], cnt_all[k:k + 1]
                 if overflow is not None:
                     overflow = overflow | (cnt[0] > cap)
                 m_host = None
@@ -189,7 +190,7 @@ class MipNerfModel:
             fuse = bf16 and self.fuse_raymarch and (self.max_deg_point - self.min_deg_point) == 10 and N == 128
             if i_level > 0:
                 t_vals = ops.resample(t_vals, weights, u_rand=rb['u_rand'], padding=self.resample_padding)
-            rm_kw = dict(contract=self.contraction, ray_mult=bg_mult, min_deg=self.min_deg_point, max_deg=self.max_deg_point,
+            rm_kw = dict(contract=self.contraction, ray_mult=bg_mult, ray_mult_is_nhit=True, min_deg=self.min_deg_point, max_deg=self.max_deg_point,
                          ray_shape=self.ray_shape, integrate=not self.disable_integration)
             if i_level == 0:
                 rm_kw.update(near=rays.near, far=rays.far, t_rand=rb['t_rand'])
@@ -487,8 +488,9 @@ class Variables:
         """(Re)build the tensor-core weight images after the parameters changed."""
         if not self._dirty and self.packed:
             return
-        for name, t in self.topo.items():
-            self.packed[name] = ops.mlp_pack(t, self.blob(name), self.packed.get(name))
+        names = list(self.topo)
+        images = ops.mlp_pack_multi([self.topo[n] for n in names], [self.blob(n) for n in names], [self.packed.get(n) for n in names])
+        self.packed.update(zip(names, images))
         self._dirty = False
 
     def to_flax_dict(self) -> Dict[str, Any]:

@@ -105,6 +105,15 @@ def compact_hits(hit: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]
     return idx, cnt
 
 
+def compact_hits_all(hit: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """`compact_hits` for every object in one launch: (ray_index int32[K,B], count int32[K])."""
+    B, K = hit.shape
+    idx = torch.empty(K, B, device=hit.device, dtype=torch.int32)
+    cnt = torch.empty(K, device=hit.device, dtype=torch.int32)
+    check(L.load().durf_compact_hits_all(stream_ptr(), B, K, ptr(hit), ptr(idx), ptr(cnt)), "durf_compact_hits_all")
+    return idx, cnt
+
+
 def mlp_merge_raw(src_rgb, src_density, ray_index, count, raw_rgb, raw_density) -> None:
     """raw[ray_index[m]] += src[m] for the rows of an object network evaluated with `mlp_fwd(..., accumulate=2)`."""
     M, N = src_density.shape
@@ -115,7 +124,7 @@ def mlp_merge_raw(src_rgb, src_density, ray_index, count, raw_rgb, raw_density) 
 # ---- K1 ---------------------------------------------------------------------------------------------
 def raymarch(origins, dirs, radii, N: int, *, t_vals=None, near=None, far=None, t_rand=None, contract=False,
              weighted=False, alpha=0.0, min_deg=0, max_deg=10, ray_shape='cone', integrate=True, ray_mult=None,
-             ray_index=None, count=None, rows=None, bf16_tiles=False, want_gaussians=False):
+             ray_index=None, count=None, rows=None, bf16_tiles=False, want_gaussians=False, ray_mult_is_nhit=False):
     """Fused sample/cast/contract/encode.  Returns dict(t_vals, features, [means, cov_diag])."""
     if ray_shape not in ('cone', 'cylinder'):
         raise AssertionError("ray_shape must be 'cone' or 'cylinder'")          # mip.py:176 `assert False`
@@ -138,6 +147,7 @@ def raymarch(origins, dirs, radii, N: int, *, t_vals=None, near=None, far=None, 
     if ray_shape == 'cylinder': flags |= L.RM_CYLINDER
     if not integrate: flags |= L.RM_NO_INTEGRATE
     if bf16_tiles: flags |= L.RM_OUT_BF16_TILE
+    if ray_mult_is_nhit and ray_mult is not None: flags |= L.RM_MULT_IS_NHIT
     F = 6 * (max_deg - min_deg) + (3 if weighted else 0)
     M = B if rows is None else rows          # rows of the output buffers (compacted calls may pass fewer)
     if bf16_tiles:
@@ -214,6 +224,30 @@ def mlp_pack(topo, blob: torch.Tensor, packed: Optional[torch.Tensor] = None) ->
     return packed
 
 
+def mlp_pack_multi(topos, blobs, packed_list):
+    """`mlp_pack` for several networks in ONE kernel launch (the background MLP and every BoxMLP after an optimizer step).
+    `packed_list` entries may be None (allocated here).  Returns the list of weight images."""
+    lib = L.load()
+    ts = [topology(t) for t in topos]
+    out = []
+    for t, blob, pk in zip(ts, blobs, packed_list):
+        if pk is None:
+            nbytes = int(lib.durf_mlp_packed_bytes(C.byref(t)))
+            if nbytes <= 0:
+                raise L.DurfError("this MLP topology has no tensor-core path")
+            pk = torch.empty(nbytes, device=_dev(blob), dtype=torch.uint8)
+        out.append(pk)
+    n = len(ts)
+    if n == 0:
+        return out
+    arr_t = (L.MlpTopology * n)(*ts)
+    blobs = [f32(b) for b in blobs]
+    arr_p = (C.c_void_p * n)(*[b.data_ptr() for b in blobs])
+    arr_k = (C.c_void_p * n)(*[k.data_ptr() for k in out])
+    check(lib.durf_mlp_pack_weights_multi(stream_ptr(), n, arr_t, arr_p, arr_k), "durf_mlp_pack_weights_multi")
+    return out
+
+
 def _mlp_args(topo, precision, M, N, features, cond, blob, packed, ray_index, count, accumulate, raw_rgb, raw_density, saved,
               workspace, fused=None, saved_offset=0, saved_total=0):
     return L.MlpArgs(topo=topology(topo), precision=precision, M=M, N=N, features=ptr(features), cond=ptr(cond),
@@ -226,7 +260,7 @@ def _mlp_args(topo, precision, M, N, features, cond, blob, packed, ray_index, co
 
 def fused_raymarch_args(origins, dirs, radii, N: int, *, t_vals=None, near=None, far=None, t_rand=None, contract=False,
                         weighted=False, alpha=0.0, min_deg=0, max_deg=10, ray_shape='cone', integrate=True, ray_mult=None,
-                        store_t_vals=True):
+                        store_t_vals=True, ray_mult_is_nhit=False):
     """The arguments of `raymarch` as a struct for `mlp_fwd(..., fused=...)` (the tcgen05 MLP kernel generates its
     own input tiles).  Returns (struct, t_vals, keepalive): t_vals is allocated here when it is to be sampled.
     `store_t_vals=False` (sampling only): the fenceposts are formed in registers and not written (t_vals is None) -- an
@@ -254,6 +288,7 @@ def fused_raymarch_args(origins, dirs, radii, N: int, *, t_vals=None, near=None,
     if ray_shape == 'cylinder': flags |= L.RM_CYLINDER
     if not integrate: flags |= L.RM_NO_INTEGRATE
     flags |= L.RM_OUT_BF16_TILE
+    if ray_mult_is_nhit and ray_mult is not None: flags |= L.RM_MULT_IS_NHIT     # multiplier = 1 - nhit (obbpose_model.py:205)
     alpha_dev = alpha if torch.is_tensor(alpha) else None
     keep = (origins, dirs, radii, near, far, t_rand, t_vals, ray_mult, alpha_dev)
     a = L.RaymarchArgs(B=B, N=N, min_deg=min_deg, max_deg=max_deg, flags=flags, alpha=0.0 if alpha_dev is not None else float(alpha),

@@ -41,14 +41,19 @@ class TrainState:
 @dataclass
 class StepScalars:
     """Per-step scalars in device memory: what changes from one replay of a captured step to the next."""
-    f: torch.Tensor          # float32[4]: lr, eps, alpha, (unused)
-    step: torch.Tensor       # int32[1]: 0-based optimizer step (incremented on the device)
+    f: torch.Tensor          # float32[4]: lr, eps, alpha, and the bits of `step`
+    step: torch.Tensor       # int32[1] view of f[3]: 0-based optimizer step
     ts: torch.Tensor         # int64[1]: timestep row of box_centers
+    # True: the Adam launch increments `step` (one more one-thread kernel per step); False: the host uploads it with the
+    # other scalars before every replay (GraphedTrainStep does, in the same 16-byte copy)
+    advance_on_device: bool = True
 
     @staticmethod
-    def create(device, step: int = 0) -> "StepScalars":
-        return StepScalars(torch.zeros(4, device=device), torch.full((1,), step, device=device, dtype=torch.int32),
-                           torch.zeros(1, device=device, dtype=torch.int64))
+    def create(device, step: int = 0, advance_on_device: bool = True) -> "StepScalars":
+        f = torch.zeros(4, device=device)
+        s = f[3:4].view(torch.int32)
+        s.fill_(step)
+        return StepScalars(f, s, torch.zeros(1, device=device, dtype=torch.int64), advance_on_device)
 
     lr = property(lambda self: self.f[0:1])
     eps = property(lambda self: self.f[1:2])
@@ -59,7 +64,7 @@ _STAT_NAMES = ('losses', 'd_losses', 'n_losses', 'e_losses', 's_losses', 'distr_
 
 
 def loss_and_grads(model: MipNerfModel, config: Config, ret, batch: Dict[str, torch.Tensor], eps, tv=None, weight_l2=None,
-                   workspace: Optional[dict] = None):
+                   workspace: Optional[dict] = None, norms: Optional[torch.Tensor] = None):
     """train_boxpose.py:94-220 for every level: returns (stats dict of device scalars, per-level gradient dicts).
     stats['loss'] is the total loss (tv and weight_l2 terms included); the per-term arrays keep the reference's names."""
     dev = ret[0][0].device
@@ -69,7 +74,8 @@ def loss_and_grads(model: MipNerfModel, config: Config, ret, batch: Dict[str, to
     if 'reduce_ws' not in ws or ws.get('reduce_B') != B:
         ws['reduce_ws'], ws['reduce_B'] = ops.losses_reduce_ws(B, dev), B
     partials = torch.empty(nl * L.LP_STRIDE, device=dev)
-    norms = torch.zeros(nl, 4, device=dev)
+    if norms is None:                   # [nl,4] zeros (train_step hands in a slice of the buffer it zeroes once per step)
+        norms = torch.zeros(nl, 4, device=dev)
     depth_mask = torch.empty(B, device=dev)
     lb = dict(pixels=ops.f32(batch['pixels'])[..., :3].contiguous(), depth=ops.f32(batch['depth']).reshape(-1),
               sky=ops.f32(batch['sky']).reshape(-1), lossmult=ops.f32(batch['rays'].lossmult).reshape(-1) if not
@@ -90,7 +96,7 @@ def loss_and_grads(model: MipNerfModel, config: Config, ret, batch: Dict[str, to
                             partials=L.ptr(partials), norms=L.ptr(norms), tv=L.ptr(tv), weight_l2=L.ptr(weight_l2), stats=L.ptr(out))
     L.check(L.load().durf_losses_finalize(L.stream_ptr(), C.byref(fa)), "durf_losses_finalize")
     per = out[:nl * L.LS_STRIDE].view(nl, L.LS_STRIDE)
-    stats = {name: per[:, i] for i, name in enumerate(_STAT_NAMES)}
+    stats = Stats({name: per[:, i] for i, name in enumerate(_STAT_NAMES)})
     stats['loss'] = out[nl * L.LS_STRIDE]
     stats['weight_l2'] = out[nl * L.LS_STRIDE + 1]
     return stats, grads
@@ -111,7 +117,11 @@ def train_step(model: MipNerfModel, config: Config, rng, state: TrainState, batc
     eps_ = scalars.eps if dev_mode else eps
     ret = model.apply(v, rng, batch['rays'], batch.get('init'), batch['ext'], ts, randomized=config.randomized,
                       rand_bkgd=config.rand_bkgd, white_bkgd=config.white_bkgd, alpha=alpha_, ctx=ctx)
-    d_flat = torch.zeros_like(v.flat)
+    # one zero-fill per step: the flat gradient, the squared gradient norm and the loss kernels' normalisers
+    n_flat, nl = v.flat.numel(), len(ret)
+    n_pad = (n_flat + 3) // 4 * 4
+    zeros = torch.zeros(n_pad + 4 + 4 * nl, device=v.flat.device)
+    d_flat, sumsq, norms = zeros[:n_flat], zeros[n_pad:n_pad + 1], zeros[n_pad + 4:].view(nl, 4)
     tv = wl2 = None
     pose = ret[0][7][0]                                                       # box_pose[0] of this timestep, [K,3]
     if prev is not None:
@@ -127,7 +137,7 @@ def train_step(model: MipNerfModel, config: Config, rng, state: TrainState, batc
         n = v.flat.numel()
         wl2 = (config.weight_decay_mult / n) * (v.flat * v.flat).sum().reshape(1)
         d_flat.add_(v.flat, alpha=2.0 * config.weight_decay_mult / n)
-    stats, grads = loss_and_grads(model, config, ret, batch, eps_, tv=tv, weight_l2=wl2, workspace=workspace)
+    stats, grads = loss_and_grads(model, config, ret, batch, eps_, tv=tv, weight_l2=wl2, workspace=workspace, norms=norms)
     # jax.lax.pmean(grad, 'batch') (:253): per-network buckets all-reduced on a side stream while the backward continues
     # (DURF_ALLREDUCE=single: one all-reduce of the whole flat gradient after the backward, the round-1 behaviour)
     bucketed = world_size > 1 and os.environ.get('DURF_ALLREDUCE', 'buckets') == 'buckets'
@@ -140,18 +150,28 @@ def train_step(model: MipNerfModel, config: Config, rng, state: TrainState, batc
             scale = 1.0 / world_size
         else:
             scale = parallel.allreduce_gradients(d_flat) if world_size > 1 else 1.0
-    sumsq = torch.zeros(1, device=d_flat.device)
     ops.grad_sanitize(d_flat, config.grad_max_val, scale, sumsq)
     if dev_mode:
-        ops.adam_step(v.flat, d_flat, state.m, state.v, sumsq, max_norm=config.grad_max_norm, lr=scalars.lr, step=scalars.step)
+        ops.adam_step(v.flat, d_flat, state.m, state.v, sumsq, max_norm=config.grad_max_norm, lr=scalars.lr, step=scalars.step,
+                      advance_step=scalars.advance_on_device)
     else:
         ops.adam_step(v.flat, d_flat, state.m, state.v, sumsq, max_norm=config.grad_max_norm, lr=lr, step=state.step)
     v.mark_dirty()
     state.step += 1
-    stats['grad_norm'] = torch.sqrt(sumsq[0])
+    stats['grad_norm_sq'] = sumsq[0]           # |g|^2 after nan_to_num / clip; stats['grad_norm'] takes the root when it is read
     stats['grad'] = d_flat
     stats['pose'] = pose                       # the forward pass's pose (stats.pose, :255): what `prevs` is updated with
     return state, stats
+
+
+class Stats(dict):
+    """The step's statistics.  stats['grad_norm'] (train_boxpose.py:283) is formed from 'grad_norm_sq' when it is read, not as
+    one more kernel of every step."""
+
+    def __missing__(self, key):
+        if key == 'grad_norm':
+            return torch.sqrt(self['grad_norm_sq'])
+        raise KeyError(key)
 
 
 def _add_box_grad(v: Variables, d_flat: torch.Tensor, ctx: dict, g: torch.Tensor, cols: slice) -> None:
@@ -189,7 +209,7 @@ class GraphedTrainStep:
         if model.density_noise > 0:
             self.rand['density_noise'] = [torch.zeros(B, N, device=dev) for _ in range(model.num_levels)]
         self.prev = torch.zeros(1, K, 6, device=dev) if use_prev else None
-        self.scalars = StepScalars.create(dev, step=state.step)
+        self.scalars = StepScalars.create(dev, step=state.step, advance_on_device=False)
         self.workspace: dict = {}
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.kernels_per_replay = 0
@@ -215,8 +235,9 @@ class GraphedTrainStep:
         if self.prev is not None and prev is not None:
             self.prev.copy_(torch.as_tensor(prev).reshape(self.prev.shape), non_blocking=True)
         ts = int(torch.as_tensor(batch['ts']).reshape(-1)[0])
-        host = torch.tensor([float(lr), float(eps), float(alpha), 0.0], dtype=torch.float32).pin_memory()
-        self.scalars.f.copy_(host, non_blocking=True)
+        host = torch.tensor([float(lr), float(eps), float(alpha), 0.0], dtype=torch.float32)
+        host.view(torch.int32)[3] = self.state.step                 # the 0-based step this replay's Adam uses
+        self.scalars.f.copy_(host.pin_memory(), non_blocking=True)
         self.scalars.ts.copy_(torch.tensor([ts], dtype=torch.int64).pin_memory(), non_blocking=True)
 
     def _eager(self):

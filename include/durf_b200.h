@@ -113,6 +113,8 @@ int durf_mlp_merge_raw(durf_stream_t stream, int32_t M, int32_t N, const int32_t
  * results back per ray) and *count their number. */
 int durf_compact_hits(durf_stream_t stream, int32_t B, int32_t K, int32_t k, const int32_t* hit,
                       int32_t* ray_index, int32_t* count);
+/* All K objects in one launch: ray_index [K,B] (row k = the list of object k), count [K]. */
+int durf_compact_hits_all(durf_stream_t stream, int32_t B, int32_t K, const int32_t* hit, int32_t* ray_index, int32_t* count);
 
 /* ---- N2: pinhole ray generation ------------------------------------------------------------ */
 typedef struct DurfCamera {
@@ -138,6 +140,8 @@ int durf_generate_rays(durf_stream_t stream, const DurfCamera* cam, int32_t row0
 #define DURF_RM_CYLINDER      (1u << 4)  /* ray_shape == 'cylinder' (mip.py:133-152) */
 #define DURF_RM_NO_INTEGRATE  (1u << 5)  /* disable_integration: zero covariances (obbpose_model.py:164-165) */
 #define DURF_RM_OUT_BF16_TILE (1u << 6)  /* features as bf16 128x64 SWIZZLE_128B tile images (input of the tcgen05 MLP) */
+#define DURF_RM_MULT_IS_NHIT  (1u << 8)  /* ray_mult holds the front-end's nhit (number of boxes the ray hits): the multiplier is
+                                            1 - nhit, the background's `1 - sum_k mask_k` (obbpose_model.py:205) */
 #define DURF_RM_NO_TVALS_OUT  (1u << 7)  /* fused_raymarch only, with DURF_RM_SAMPLE: the fenceposts are formed but not stored (t_vals may
                                             be NULL): an object network evaluated next to the background network, which stores them */
 
@@ -181,6 +185,10 @@ int durf_viewdir_enc_fwd(durf_stream_t stream, int32_t B, int32_t deg, const flo
 int64_t durf_mlp_packed_bytes(const DurfMlpTopology* topo);
 /* fp32 parameter blob -> tensor-core weight image.  Call again after every optimizer step. */
 int durf_mlp_pack_weights(durf_stream_t stream, const DurfMlpTopology* topo, const float* params, void* packed);
+/* The same for n networks (the background MLP and every BoxMLP after an optimizer step) in ONE kernel launch:
+ * topos[n] (an array of structs), params[n], packed[n]. */
+int durf_mlp_pack_weights_multi(durf_stream_t stream, int32_t n, const DurfMlpTopology* topos, const float* const* params,
+                                void* const* packed);
 
 typedef struct DurfMlpArgs {
   DurfMlpTopology topo;
