@@ -73,6 +73,24 @@ static ffi::Error CompactHitsImpl(cudaStream_t stream, S32 hit, int32_t k, RS32 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(DurfCompactHits, CompactHitsImpl,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<S32>().Attr<int32_t>("k").Ret<S32>().Ret<S32>());
 
+static ffi::Error CompactHitsAllImpl(cudaStream_t stream, S32 hit, RS32 ray_index, RS32 count) {
+  return Check(durf_compact_hits_all(stream, Dim(hit, 0), Dim(hit, 1), hit.typed_data(), ray_index->typed_data(), count->typed_data()));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DurfCompactHitsAll, CompactHitsAllImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<S32>().Ret<S32>().Ret<S32>());
+
+// raw[ray_index[m]] += src[m] for an object network evaluated into compact rows (DurfMlpArgs.accumulate == 2): the per-ray
+// buffers are operands aliased to the results (input_output_aliases={4: 0, 5: 1}).
+static ffi::Error MlpMergeRawImpl(cudaStream_t stream, F32 src_rgb, F32 src_density, S32 ray_index, S32 count, F32 raw_rgb_in,
+                                  F32 raw_density_in, RF32 raw_rgb, RF32 raw_density) {
+  (void)raw_rgb_in; (void)raw_density_in;            // same buffers as the results
+  return Check(durf_mlp_merge_raw(stream, Dim(src_density, 0), Dim(src_density, 1), ray_index.typed_data(), OrNull(count),
+                                  src_rgb.typed_data(), src_density.typed_data(), raw_rgb->typed_data(), raw_density->typed_data()));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DurfMlpMergeRaw, MlpMergeRawImpl,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Arg<F32>().Arg<F32>().Arg<S32>().Arg<S32>()
+                                  .Arg<F32>().Arg<F32>().Ret<F32>().Ret<F32>());
+
 // ---- K1: mip.sample_along_rays | resampled t_vals -> cast_rays -> mip360.new_space -> integrated_pos_enc | weighted_ipe
 // (mip.py:330-370, 155-179, 226-282, 182-223; mip360.py:63-79).  t_vals is an OPERAND aliased to the first result
 // (input_output_aliases={7: 0}): read when DURF_RM_SAMPLE is clear, written when it is set.  `features` is fp32 [M,N,F] or,

@@ -10,7 +10,8 @@ exposes differentiable functions with the argument meaning of the reference's ca
     DurfMlpFwdFused (N1)            DurfMlpBwd              background_mlp_fused (d params; the rays carry no gradient)
     DurfCompositeFwd                DurfCompositeBwd        volumetric_rendering_raw (d raw_rgb, d raw_density, d dirs_s)
     DurfResampleFwd                 - (stop_gradient, mip.py:413-414)           resample_along_rays_t
-    DurfViewdirEnc, DurfCompactHits, DurfMlpPack            - (no differentiable inputs)
+    DurfViewdirEnc, DurfCompactHits, DurfCompactHitsAll, DurfMlpPack            - (no differentiable inputs)
+    DurfMlpMergeRaw                 - (linear: the cotangent of the compact rows is a gather)   merge_raw
 
 Needs a JAX with `jax.ffi` (>= 0.4.38).  The build image of this repository has no jax, so nothing here is executed by its
 tests; `tests/test_ffi_shim.py` checks what can be checked without it: every handler named here is defined in durf_ffi.cc
@@ -30,6 +31,8 @@ HANDLERS = {
     "DurfObbFrontendFwd": (4, 0, 7),
     "DurfObbFrontendBwd": (7, 2, 1),
     "DurfCompactHits": (1, 1, 2),
+    "DurfCompactHitsAll": (1, 0, 2),
+    "DurfMlpMergeRaw": (6, 0, 2),
     "DurfRaymarchFwd": (10, 5, 2),
     "DurfRaymarchBwd": (9, 5, 2),
     "DurfViewdirEnc": (1, 1, 1),
@@ -117,6 +120,25 @@ def compact_hits(hit, k):
     import jax.numpy as jnp
     B = hit.shape[0]
     return jax.ffi.ffi_call("DurfCompactHits", (jax.ShapeDtypeStruct((B,), jnp.int32), jax.ShapeDtypeStruct((1,), jnp.int32)))(hit, k=int(k))
+
+
+def compact_hits_all(hit):
+    """`compact_hits` for every object in one custom call: (ray_index [K,B], count [K])."""
+    import jax
+    import jax.numpy as jnp
+    B, K = hit.shape
+    return jax.ffi.ffi_call("DurfCompactHitsAll", (jax.ShapeDtypeStruct((K, B), jnp.int32), jax.ShapeDtypeStruct((K,), jnp.int32)))(hit)
+
+
+def merge_raw(raw_rgb, raw_density, src_rgb, src_density, ray_index, count):
+    """raw[ray_index[m]] += src[m] (m < count): adds the compact outputs of an object network evaluated with accumulate = 2
+    into the per-ray buffers -- `raw += mask_k * BoxMLP_k(...)` (obbpose_model.py:203-204, 233-234) without making the
+    network's call depend on the buffers.  Linear in (raw, src); call it outside differentiated code or wrap it with the
+    gather as its cotangent."""
+    import jax
+    outs = (jax.ShapeDtypeStruct(raw_rgb.shape, raw_rgb.dtype), jax.ShapeDtypeStruct(raw_density.shape, raw_density.dtype))
+    return jax.ffi.ffi_call("DurfMlpMergeRaw", outs, input_output_aliases={4: 0, 5: 1})(src_rgb, src_density, ray_index, count,
+                                                                                      raw_rgb, raw_density)
 
 
 # ---- K1 ------------------------------------------------------------------------------------------------------------
