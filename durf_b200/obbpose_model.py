@@ -83,7 +83,9 @@ class MipNerfModel:
     # == 2; at level 0 it re-forms the fenceposts itself, DURF_RM_NO_TVALS_OUT) that durf_mlp_merge_raw adds into the per-ray
     # outputs in object order afterwards - the sums of the serial path bit for bit.  At the reference's 512-ray batch the
     # background network is 3.5 waves of tiles: the objects' tiles run on the SMs its last wave leaves idle.
-    concurrent_objects: bool = field(default_factory=lambda: os.environ.get('DURF_OBJ_CONCURRENT', '1') != '0')
+    # None (default, DURF_OBJ_CONCURRENT unset): only while the step is being captured into a CUDA graph - launched from Python
+    # a 512-ray step is bound by the host, and the extra stream switches cost it 0.15 ms.
+    concurrent_objects: Optional[bool] = field(default_factory=lambda: {'0': False, '1': True}.get(os.environ.get('DURF_OBJ_CONCURRENT')))
     concurrent_objects_max_rays: int = 4096
     shared_level_max_rays: int = 4096
     overlap_min_rays: int = 2048
@@ -197,7 +199,8 @@ class MipNerfModel:
             else:
                 rm_kw.update(t_vals=t_vals)
             # object networks next to the background network (see `concurrent_objects`)
-            conc = (fuse and self.dynamics and obj_prec == L.PREC_BF16 and self.concurrent_objects and K > 0
+            want_conc = self.concurrent_objects if self.concurrent_objects is not None else torch.cuda.is_current_stream_capturing()
+            conc = (fuse and self.dynamics and obj_prec == L.PREC_BF16 and want_conc and K > 0
                     and B <= self.concurrent_objects_max_rays)
             pending = []
             if conc:
@@ -293,6 +296,12 @@ class MipNerfModel:
                 lvl_ctx.update(raw_rgb=raw_rgb, raw_density=raw_density, t_vals=t_vals)
                 ctx['levels'].append(lvl_ctx)
         return ret
+
+    def step_is_capturable(self) -> bool:
+        """True if a train step of this model makes no host read (train.GraphedTrainStep can capture it): the tensor-core
+        path sizes the object networks' work from device counts; the fp32 parity kernels are sized on the host."""
+        pose_train = self.dynamics and not (self.no_pose_opt and self.no_yaw_opt)
+        return self.precision == 'bf16' and not (pose_train and self.box_net_width != 128)
 
     # -- backward ----------------------------------------------------------------------------------------
     def backward(self, variables: "Variables", ctx: dict, level_grads: Sequence[dict], d_flat: torch.Tensor,

@@ -21,7 +21,7 @@ import torch
 
 from . import checkpoint, math as dmath, obbpose_dataset, parallel, synthetic as S
 from .obbpose_model import MipNerfModel, Variables, render_camera
-from .train import TrainState, train_step
+from .train import GraphedTrainStep, TrainState, train_step
 from .utils import Config, Rays, load_gin
 
 
@@ -85,6 +85,7 @@ def main(argv=None) -> Dict:
     ap.add_argument("--print_every", type=int, default=100)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--render_rows", type=int, default=0, help="rows of the final 1920-wide test render (0: none)")
+    ap.add_argument("--no_graph", action="store_true", help="launch every step from Python instead of replaying it from a CUDA graph")
     ap.add_argument("--data_dir", default=None, help="an on-disk CARLA scene (internal/obbpose_dataset.py layout); default: synthetic batches")
     args = ap.parse_args(argv)
 
@@ -120,11 +121,20 @@ def main(argv=None) -> Dict:
                                                config.alpha_max_steps)
     prevs = torch.from_numpy(np.asarray(dataset.peek()["init"], np.float32)).to(dev)
     t0, losses, last = time.time(), [], {}
+    # The step is captured once in a CUDA graph and replayed (at the reference's shipped batch of 512 rays launching its ~40
+    # kernels from Python takes longer than running them); the fp32 parity mode sizes its GEMMs on the host and is not capturable.
+    graphed, use_graph = None, not args.no_graph and model.step_is_capturable()
     for step, batch in zip(range(init_step, config.max_steps + 1), dataset):
         ts = batch["ts"]
         prev = prevs[ts + 1 if ts == 0 else ts - 1][None]                        # train_boxpose.py:453-456
-        state, stats = train_step(model, config, None, state, batch, lr_fn(step), eps_fn(step), alpha_fn(step), prev=prev,
-                                  world_size=world)
+        if use_graph and graphed is None:
+            graphed = GraphedTrainStep(model, config, state, batch['rays'][0].shape[0], variables.K, world_size=world, device=dev,
+                                       use_prev=True)
+        if graphed is not None:
+            stats = graphed(batch, lr_fn(step), eps_fn(step), alpha_fn(step), prev=prev)
+        else:
+            state, stats = train_step(model, config, None, state, batch, lr_fn(step), eps_fn(step), alpha_fn(step), prev=prev,
+                                      world_size=world)
         prevs[ts, :, :3] = stats['pose']              # the FORWARD pass's pose (stats.pose), not the post-Adam one (:461)
         state.step = step
         if step % args.print_every == 0 or step == config.max_steps:
