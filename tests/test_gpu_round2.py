@@ -386,3 +386,48 @@ def test_two_gpu_allreduced_gradient_is_the_mean_of_rank_gradients(tmp_path):
     assert err <= 1e-6 * float(want.abs().max()), err
     assert torch.equal(outs[0]['multi'], outs[1]['multi'])
     assert torch.equal(outs[0]['params'], outs[1]['params'])
+
+
+def test_merged_launch_entry_points_equal_their_single_forms():
+    """durf_compact_hits_all == durf_compact_hits per object (as sets: the lists are unordered), durf_mlp_pack_weights_multi ==
+    durf_mlp_pack_weights per network (byte for byte), durf_mlp_merge_raw == an index_add of the compact rows (bit for bit,
+    rows beyond the device count untouched), and the ray multiplier formed in the kernel (DURF_RM_MULT_IS_NHIT) == the
+    multiplier 1 - nhit handed in (obbpose_model.py:205)."""
+    from durf_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(5)
+    B, K, N = 777, 3, 128
+    hit = (torch.rand(B, K, device='cuda', generator=g) < 0.3).int()
+    idx_all, cnt_all = ops.compact_hits_all(hit)
+    for k in range(K):
+        idx, cnt = ops.compact_hits(hit, k)
+        n = int(cnt)
+        assert n == int(cnt_all[k]) == int(hit[:, k].sum())
+        assert torch.equal(idx[:n].sort().values, idx_all[k, :n].sort().values)
+        assert torch.equal(idx_all[k, :n].sort().values, torch.nonzero(hit[:, k]).flatten().int())
+    # pack: two topologies, three networks
+    topos = [(60, 256, 8, 4, 27, 128), (63, 128, 8, 4, 27, 128), (63, 128, 8, 4, 27, 128)]
+    blobs = [torch.randn(ops.mlp_param_count(t), device='cuda', generator=g) * 0.1 for t in topos]
+    multi = ops.mlp_pack_multi(topos, blobs, [None] * 3)
+    for t, b, m in zip(topos, blobs, multi):
+        assert torch.equal(ops.mlp_pack(t, b), m)
+    # merge
+    rows, n_valid = 200, 150
+    src_rgb = torch.randn(rows, N, 3, device='cuda', generator=g)
+    src_den = torch.randn(rows, N, device='cuda', generator=g)
+    raw_rgb = torch.randn(B, N, 3, device='cuda', generator=g)
+    raw_den = torch.randn(B, N, device='cuda', generator=g)
+    ray_index = torch.randperm(B, device='cuda', generator=g)[:rows].int()
+    count = torch.tensor([n_valid], device='cuda', dtype=torch.int32)
+    want_rgb, want_den = raw_rgb.clone(), raw_den.clone()
+    want_rgb[ray_index[:n_valid].long()] += src_rgb[:n_valid]
+    want_den[ray_index[:n_valid].long()] += src_den[:n_valid]
+    ops.mlp_merge_raw(src_rgb, src_den, ray_index, count, raw_rgb, raw_den)
+    assert torch.equal(raw_rgb, want_rgb) and torch.equal(raw_den, want_den)
+    # multiplier from nhit
+    sc = H.scene(B=300, K=2, seed=12)
+    cr = H.cuda_rays(sc)
+    nhit = torch.randint(0, 3, (300,), device='cuda', generator=g).float()
+    kw = dict(near=cr.near, far=cr.far, contract=True)
+    a = ops.raymarch(cr.origins, cr.directions, cr.radii, N, ray_mult=1.0 - nhit, **kw)
+    b = ops.raymarch(cr.origins, cr.directions, cr.radii, N, ray_mult=nhit, ray_mult_is_nhit=True, **kw)
+    assert torch.equal(a['features'], b['features']) and torch.equal(a['t_vals'], b['t_vals'])
