@@ -14,7 +14,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdurf_b200.so")
+# DURF_B200_LIB: another build of the library (e.g. one made with `make EXTRA=-DDURF_TRACE=1`)
+LIB_PATH = os.environ.get("DURF_B200_LIB") or os.path.join(_HERE, "libdurf_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK = 0

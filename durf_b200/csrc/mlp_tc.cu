@@ -400,7 +400,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
       IssueState st{0u, 0u, 0u};
       uint32_t inp_par = 0;
       int it = 0;
-      const bool tr = p.trace && blockIdx.x == 0;
+      const bool tr = DURF_TRACE && p.trace && blockIdx.x == 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       long long t_start = 0, t_begin = clock64(), tq = 0;
       const uint32_t inp_lo = ((sbase + C::OFF_INP) & 0x3FFFF) >> 4 | (1u << 16);
@@ -546,7 +546,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
     // miss a phase.)  Weight ring stages are released by the MMA issuer's own commits.
     const bool releaser = threadIdx.x == 128;
     uint32_t stg_buf = 0;                         // SAVE: which of this warp's two 4 KB staging pieces the next epilogue fills
-    const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 128;
+    const bool tr = DURF_TRACE && p.trace && blockIdx.x == 0 && threadIdx.x == 128;
     long long e_acc = 0, e_ld = 0, e_math = 0, e_st = 0, e_begin = clock64(), eq = 0, e_m0 = 0, e_ld1 = 0, e_m1 = 0;
     const bool trs = DURF_TRACE_DETAIL && tr;
     long long sv_wg = 0, sv_fill = 0, sv_fence = 0, sv_issue = 0, sq = 0;

@@ -10,6 +10,11 @@
 #ifndef DURF_TRACE_DETAIL
 #define DURF_TRACE_DETAIL 0
 #endif
+// The forward kernel's own counters (DURF_TC_TRACE=1: where block 0's MMA thread and one epilogue thread spent their cycles)
+// need `make EXTRA=-DDURF_TRACE=1`: even switched off at run time their ~25 predicated instructions per epilogue issue.
+#ifndef DURF_TRACE
+#define DURF_TRACE DURF_TRACE_DETAIL
+#endif
 
 namespace durf {
 
