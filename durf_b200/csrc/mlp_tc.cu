@@ -312,7 +312,7 @@ mlp_tc_fwd_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;      // warp-uniform for the compiler (uniform registers, uniform branches)
   // CTAs of a cluster (1 or 2, chosen at launch) walk their tiles in lock step and share every weight fetch: each loads
   // 1/nct of a ring stage and multicasts it, so the L2 -> SM weight traffic per tile drops by nct.
   const uint32_t nct = cluster_nctarank(), crank = cluster_ctarank();

@@ -144,7 +144,7 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;      // warp-uniform for the compiler
   float* s_wden = reinterpret_cast<float*>(smem + C::OFF_WDEN);   // filled below, read with ld.shared
   float* s_wrgb = reinterpret_cast<float*>(smem + C::OFF_WRGB);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::OFF_MISC);
