@@ -80,7 +80,7 @@ mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;      // warp-uniform for the compiler
   constexpr int OFF_MISC = kWgStages * kWgStageBytes;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + OFF_MISC);
   const uint32_t bar0 = sbase + OFF_MISC + 16;
