@@ -328,7 +328,13 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
     int pq[kPubDepth];
 #pragma unroll
     for (int i = 0; i < kPubDepth; ++i) pq[i] = -1;
-    const uint32_t* s_epi = reinterpret_cast<const uint32_t*>(smem + C::OFF_EPI);      // stage table, see epi_word
+    // stage table (see the word's layout above): read with ld.shared and broadcast from lane 0, so that the compiler knows the
+    // word - and the stage kind, slot and flags decoded from it - is warp-uniform (uniform branches, uniform store addresses)
+    auto s_epi = [&](int i) {
+      uint32_t v;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + C::OFF_EPI + 4u * (uint32_t)i));
+      return __shfl_sync(kFull, v, 0);
+    };
     const uint32_t my_out = sbase + C::OFF_OUT + ((warp - 4) << 12);
     const uint32_t row_off = (lane >> 3) * 1024 + (lane & 7) * 128, r7 = lane & 7;
     // this warp's 4 KB piece inside a layer record [sample half][64-column block][64 rows x 128 B]: `nb` blocks per half
@@ -406,10 +412,10 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
         if (lane == 0) mbar_arrive(bar_p_ready);
         staging_store(dzt + (size_t)p.cond_slot * kBlockBytes + piece_c);
       }
-      uint32_t ew = s_epi[0];
+      uint32_t ew = s_epi(0);
       for (int s = 0; s < p.n_stages; ++s) {
         const uint32_t w = ew;
-        ew = s_epi[s + 1];                             // the next stage's entry (table is padded): off the post-barrier path
+        ew = s_epi(s + 1);                             // the next stage's entry (table is padded): off the post-barrier path
         if (s + 1 == p.n_stages && tile + (int)gridDim.x < num_tiles) prefetch_tile(tile + (int)gridDim.x);
         if (!(w & 16u)) continue;                      // entries that only accumulate have no epilogue
         const int kind = w & 3, n_halves = (w >> 2) & 3, out_slot = (w >> 8) & 0xFF;
@@ -461,7 +467,7 @@ mlp_tc_dgrad_kernel(const __grid_constant__ DgParams p) {
           int h2 = h + 1;
           if (h2 >= n_halves) {                          // the next entry with an epilogue (entries are padded with zeros)
             h2 = 0; wn = ew;
-            for (int s2 = s + 2; !(wn & 16u) && s2 <= p.n_stages; ++s2) wn = s_epi[s2];
+            for (int s2 = s + 2; !(wn & 16u) && s2 <= p.n_stages; ++s2) wn = s_epi(s2);
           }
           const int mg = (wn >> 16) & 31;                // trunk layer whose ReLU mask gates that epilogue's output (31: none)
           if ((wn & 16u) && mg != 31) {
