@@ -78,7 +78,8 @@ __device__ __forceinline__ void red_add4(float* addr, float a, float b, float c,
 __global__ void __launch_bounds__(384, 1)
 mlp_tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by an OFFSET into the __shared__ array: the pointer keeps its address space (ld/st.shared, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;      // warp-uniform for the compiler
   constexpr int OFF_MISC = kWgStages * kWgStageBytes;
