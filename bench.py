@@ -620,6 +620,9 @@ def main():
     roof = dict(bound="tensor", kernel="mlp_tc_fwd_kernel<256> (ray-march fused in)", achieved=ach, peak=peaks["tf_sustained"], unit="TFLOP/s",
                 frac=ach / peaks["tf_sustained"], traffic=traffic, traffic_unit="bytes per launch (ncu dram read+write, profiles/r02_mlp_fwd_traffic.json)",
                 flops_per_launch=flops / max(n_mlp, 1), peak_source=peaks["src"] + " (sustained bf16 cuBLAS)",
+                # context: the sustained cuBLAS figure is itself power-capped (measured at a 1327 MHz median clock); the
+                # burst figure is the harder ceiling
+                peak_burst=peaks["tf_burst"], frac_of_burst=ach / peaks["tf_burst"],
                 launches=n_mlp, avg_launch_ms=mlp_ms / max(n_mlp, 1), share_of_step=mlp_ms / (ms_resident * steps))
     line = dict(metric="rays/sec (render, 2x128 samples)", value=value, unit="rays/s", n_gpus=world, steps=steps, warmup=warmup,
                 ms_per_step=ms_resident, higher_is_better=True, scaling="weak", vs_baseline=None,
