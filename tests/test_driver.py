@@ -60,3 +60,21 @@ def test_driver_trains_from_an_on_disk_scene(tmp_path):
                                      principal_point=cam["principal_point"])
         for name, host, dev in zip(dev_rays._fields, test.rays, dev_rays):
             np.testing.assert_allclose(dev.cpu().numpy().reshape(host[0].shape), host[0], rtol=1e-6, atol=1e-6, err_msg=name)
+
+
+def test_step_capturability_and_lazy_grad_norm():
+    """Host logic next to the graphed train step: which models the driver may capture (the fp32 parity mode and a box-pose
+    step whose BoxMLP is not 128 wide size their GEMMs from a host read), and stats['grad_norm'] formed on demand from the
+    squared norm the step leaves on the device (train_boxpose.py:283)."""
+    import torch
+    from durf_b200.obbpose_model import MipNerfModel
+    from durf_b200.train import Stats
+    assert MipNerfModel(precision='bf16').step_is_capturable()
+    assert not MipNerfModel(precision='fp32').step_is_capturable()
+    assert MipNerfModel(precision='bf16', no_pose_opt=False, no_yaw_opt=False).step_is_capturable()
+    assert not MipNerfModel(precision='bf16', no_pose_opt=False, box_net_width=256).step_is_capturable()
+    assert MipNerfModel(precision='bf16').concurrent_objects is None       # decided per call: only while capturing
+    st = Stats(grad_norm_sq=torch.tensor(6.25), loss=torch.tensor(1.0))
+    assert float(st['grad_norm']) == 2.5 and 'grad_norm' not in st
+    with pytest.raises(KeyError):
+        st['no_such_stat']
